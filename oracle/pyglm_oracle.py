@@ -1,0 +1,484 @@
+"""ORACLE -- test infrastructure, NOT product code.
+
+CPU restatement (numpy/scipy, float64) of the reference's sparse-Bernoulli Gibbs hot path,
+function by function, each citing the reference file:line it follows (paths relative to
+/root/reference).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; nothing under pyglm_b200/ does.
+
+Pinning: every deterministic function here is checked against fixtures produced by the
+reference's OWN files run through oracle/ref_shim (oracle/gen_golden.py -> tests/golden/*.npz,
+tests/test_oracle_golden.py), including the two assertions of the reference's test suite
+(test/test_generate.py:24 and :55) and the SURVEY Appendix-D known-answer values.
+The stochastic primitives (PG draws, Gaussian / categorical / NIW draws) have no golden vector
+in the reference and their third-party implementations are absent: PARITY UNPINNED for the
+draws themselves; their deterministic cores (Cholesky, solves, logsumexp) are pinned via
+marginal_likelihood / resample_W with injected randomness.
+
+All random inputs are injectable (omega, perm, u, z) so that the CUDA path can be compared on
+identical draws.
+"""
+import ctypes
+import os
+
+import numpy as np
+import scipy.linalg
+import scipy.signal as sig
+from scipy.linalg import block_diag
+from scipy.linalg.lapack import dpotrs
+from scipy.special import logsumexp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# --------------------------------------------------------------------------- PG sampler (C)
+_pg_lib = None
+
+
+def pg_lib():
+    """ctypes handle on oracle/libpg_oracle.so (built by oracle/Makefile / __graft_entry__.build)."""
+    global _pg_lib
+    if _pg_lib is None:
+        path = os.path.join(_HERE, "libpg_oracle.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/libpg_oracle.so missing: run `make -C oracle`")
+        lib = ctypes.CDLL(path)
+        lib.pg1_drawv.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint32,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        lib.pg_omp_max_threads.restype = ctypes.c_int
+        lib.philox_stream_unif.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64,
+                                           ctypes.c_int, ctypes.c_void_p]
+        lib.philox4x32_10.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _pg_lib = lib
+    return _pg_lib
+
+
+def pg1_draw(psi, seed, call_id=0, rng_kind=0, nthreads=0):
+    """omega_i ~ PG(1, psi_i).  Stands for pgdrawvpar(ppgs, ones, psi, out), regression.py:501-508.
+    rng_kind 0: per-element Philox stream (the stream the CUDA kernel uses); 1: per-thread RNGs."""
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    out = np.empty_like(psi)
+    pg_lib().pg1_drawv(psi.ctypes.data, psi.size, int(seed), int(call_id), int(rng_kind),
+                       int(nthreads), out.ctypes.data)
+    return out
+
+
+def philox_uniforms(seed, call_id, elem, count):
+    out = np.empty(count)
+    pg_lib().philox_stream_unif(int(seed), int(call_id), int(elem), int(count), out.ctypes.data)
+    return out
+
+
+def pg1_mean(psi):
+    """E[PG(1, psi)] = tanh(psi/2) / (2 psi), 1/4 at 0."""
+    psi = np.asarray(psi, dtype=np.float64)
+    safe = np.where(np.abs(psi) < 1e-6, 1.0, psi)
+    return np.where(np.abs(psi) < 1e-6, 0.25 - psi ** 2 / 48.0, np.tanh(safe / 2.0) / (2.0 * safe))
+
+
+def pg1_var(psi):
+    """Var[PG(1, psi)] = (sinh psi - psi) / (4 psi^3 cosh^2(psi/2)), 1/24 at 0."""
+    psi = np.asarray(psi, dtype=np.float64)
+    safe = np.where(np.abs(psi) < 1e-3, 1.0, psi)
+    v = (np.sinh(safe) - safe) / (4.0 * safe ** 3 * np.cosh(safe / 2.0) ** 2)
+    return np.where(np.abs(psi) < 1e-3, 1.0 / 24.0, v)
+
+
+# --------------------------------------------------------------------------- (1) filter build
+def cosine_basis(B, L=100, orth=False, norm=True, n_eye=0, a=1.0 / 120, b=0.5):
+    """Raised-cosine bumps on a log-time axis.  Follows pyglm/utils/basis.py:61-106."""
+    n_cos = B - n_eye
+    assert n_cos >= 0 and n_eye >= 0
+    basis = np.zeros((L, B))
+    basis[:n_eye, :n_eye] = np.eye(n_eye)
+    u_ir = np.log(a * np.arange(L) + b)                                   # :82-83
+    ctrs = u_ir[np.floor(np.linspace(n_eye, (L / 2.0), n_cos)).astype(int)]  # :84
+    if len(ctrs) == 1:
+        w = ctrs / 2                                                      # :85-86
+    else:
+        w = (ctrs[-1] - ctrs[0]) / (n_cos - 1)                            # :88
+    for i in range(n_cos):                                                # :91-93
+        arg = np.maximum(-np.pi, np.minimum(np.pi, (u_ir - ctrs[i]) * np.pi / w / 2.0))
+        basis[:, n_eye + i] = (np.cos(arg) + 1) / 2.0
+    if orth:
+        basis = scipy.linalg.orth(basis)
+    elif norm:
+        if np.any(basis < 0):
+            raise Exception("We can only normalize nonnegative impulse responses!")
+        basis = basis / np.tile(np.sum(basis, axis=0), [L, 1]) / (1.0 / L)  # :105
+    return basis
+
+
+def convolve_with_basis(S, basis):
+    """X[t,n,b] = sum_{l=1..L} basis[l-1,b] S[t-l,n].  Follows pyglm/utils/basis.py:5-34
+    (zero row prepended :18, per-b FFT convolution truncated to T :24-27, clip :30-32)."""
+    T, N = S.shape
+    R, B = basis.shape
+    basis = np.vstack((np.zeros((1, B)), basis))
+    F = np.empty((T, N, B))
+    for b in range(B):
+        F[:, :, b] = sig.fftconvolve(S, np.reshape(basis[:, b], (R + 1, 1)), 'full')[:T, :]
+    if np.amin(basis) >= 0 and np.amin(S) >= 0:
+        np.clip(F, 0, np.inf, out=F)
+    return F
+
+
+def convolve_direct(S, basis):
+    """The same filter as an explicit causal sum (what test/test_generate.py:24 pins the FFT
+    route against: generate() builds X[t] = Y[t-L:t].T.dot(flipud(basis)), models.py:121,140)."""
+    T, N = S.shape
+    L, B = basis.shape
+    X = np.zeros((T, N, B))
+    for l in range(1, L + 1):
+        if l >= T:
+            break
+        X[l:] += S[:T - l, :, None] * basis[l - 1][None, None, :]
+    return X
+
+
+# --------------------------------------------------------------------------- host helpers
+def expand_scalar(x, shp):
+    """pyglm/utils/utils.py:7-12."""
+    if np.isscalar(x):
+        x = x * np.ones(shp)
+    else:
+        assert x.shape == shp
+    return x
+
+
+def expand_cov(c, shp):
+    """pyglm/utils/utils.py:15-27."""
+    d = shp[-1]
+    if np.isscalar(c):
+        c = c * np.eye(d)
+        tshp = np.array(shp)
+        tshp[-2:] = 1
+        c = np.tile(c, tshp)
+    else:
+        assert c.shape == shp
+    return c
+
+
+def logistic(x):
+    """pyglm/utils/utils.py:3-4."""
+    return 1. / (1 + np.exp(-x))
+
+
+# --------------------------------------------------------------------------- (5) psi, LL, mean
+def flatten_X(X, N, B):
+    """regression.py:173-180: (T,N,B) -> (T, N*B), n-major / b-minor."""
+    if X.ndim == 2:
+        assert X.shape[1] == N * B
+        return X
+    return np.reshape(X, (-1, N * B))
+
+
+def activation(X, a, W, b):
+    """psi = X . vec(a o W) + b.  regression.py:195-201."""
+    N, B = W.shape
+    X = flatten_X(X, N, B)
+    w = np.reshape(a[:, None] * W, (N * B,))
+    return X.dot(w) + np.ravel(b)[0]
+
+
+def log_likelihood_terms(X, y, a, W, b):
+    """Per-bin Bernoulli log-likelihood y psi - log(1+e^psi).  regression.py:491-494 with
+    a_func=y (:515), b_func=1 (:518), c_func=1 (:521)."""
+    psi = activation(X, a, W, b)
+    return np.log(1.0) + y * psi - 1.0 * np.log1p(np.exp(psi))
+
+
+def model_log_likelihood(X, Y, A, W, bias):
+    """models.py:82-96: sum over neurons and bins."""
+    ll = 0
+    for n in range(Y.shape[1]):
+        ll += log_likelihood_terms(X, Y[:, n], A[n], W[n], bias[n:n + 1]).sum()
+    return ll
+
+
+def mean(X, a, W, b):
+    """regression.py:524-526."""
+    return logistic(activation(X, a, W, b))
+
+
+def model_means(X, A, W, bias):
+    """models.py:153-163 for one dataset -> (T, N)."""
+    return np.column_stack([mean(X, A[n], W[n], bias[n:n + 1]) for n in range(A.shape[0])])
+
+
+def kappa(y):
+    """kappa = a_func(y) - b_func(y)/2 = y - 1/2.  regression.py:510-511."""
+    return y - 0.5
+
+
+# --------------------------------------------------------------------------- (3) sufficient stats
+def lkhd_sufficient_statistics(X, omega, kap):
+    """J = [X,1]^T diag(omega) [X,1], h = [X,1]^T kappa for one dataset.  regression.py:225-262."""
+    T, NB = X.shape
+    J = np.zeros((NB + 1, NB + 1))
+    h = np.zeros(NB + 1)
+    XO = X * omega[:, None]                     # :251
+    J[:NB, :NB] += XO.T.dot(X)                  # :252
+    Xsum = XO.sum(0)                            # :253
+    J[:NB, -1] += Xsum
+    J[-1, :NB] += Xsum
+    J[-1, -1] += omega.sum()                    # :256
+    h[:NB] += kap.T.dot(X)                      # :259
+    h[-1] += kap.sum()                          # :260
+    return J, h
+
+
+def natural_params(mu_w, S_w, mu_b, S_b):
+    """regression.py:138-151."""
+    N, B = mu_w.shape
+    J_w = np.zeros((N, B, B))
+    h_w = np.zeros((N, B))
+    for n in range(N):
+        J_w[n] = np.linalg.inv(S_w[n])
+        h_w[n] = J_w[n].dot(mu_w[n])
+    J_b = np.linalg.inv(S_b)
+    h_b = J_b.dot(mu_b)
+    return J_w, h_w, J_b, h_b
+
+
+def prior_sufficient_statistics(mu_w, S_w, mu_b, S_b):
+    """regression.py:210-223."""
+    J_w, h_w, J_b, h_b = natural_params(mu_w, S_w, mu_b, S_b)
+    J_prior = block_diag(*J_w, J_b)
+    h_prior = np.concatenate((h_w.ravel(), h_b.ravel()))
+    return J_prior, h_prior
+
+
+# --------------------------------------------------------------------------- (4) spike and slab
+def _mask(a, B):
+    return np.concatenate((np.repeat(a, B), [1])).astype(bool)
+
+
+def marginal_likelihood(J_prior, h_prior, J_post, h_post, a, B):
+    """regression.py:343-378 (Cholesky form)."""
+    m = _mask(a, B)
+    J0 = J_prior[np.ix_(m, m)]
+    h0 = h_prior[m]
+    Jp = J_post[np.ix_(m, m)]
+    hp = h_post[m]
+    L0 = np.linalg.cholesky(J0)
+    Lp = np.linalg.cholesky(Jp)
+    ml = 0
+    ml -= np.sum(np.log(np.diag(Lp)))
+    ml += np.sum(np.log(np.diag(L0)))
+    ml += 0.5 * hp.T.dot(dpotrs(Lp, hp, lower=True)[0])
+    ml -= 0.5 * h0.T.dot(dpotrs(L0, h0, lower=True)[0])
+    return ml
+
+
+def sample_discrete_from_log_u(lps, u):
+    """pybasicbayes.util.stats.sample_discrete_from_log for a 1-D vector with the uniform
+    injected (regression.py:315).  Third-party restatement, SURVEY Appendix B.2."""
+    cum = np.exp(lps - logsumexp(lps)).cumsum()
+    return int(np.sum(u * cum[-1] > cum))
+
+
+def collapsed_resample_a(J_prior, h_prior, J_post, h_post, a, rho, B, perm, us, trace=None):
+    """regression.py:282-320 with the permutation (:286) and the per-step uniforms (:315)
+    injected.  Returns the new a (copy).  trace, if a list, receives (n, lp0, lp1, v)."""
+    a = np.array(a, dtype=bool).copy()
+    ml_prev = marginal_likelihood(J_prior, h_prior, J_post, h_post, a, B)
+    for step, n in enumerate(perm):
+        lps = np.zeros(2)
+        v_prev = int(a[n])
+        lps[v_prev] += ml_prev
+        lps[v_prev] += v_prev * np.log(rho[n]) + (1 - v_prev) * np.log(1 - rho[n])
+        v_new = 1 - v_prev
+        a[n] = v_new
+        ml_new = marginal_likelihood(J_prior, h_prior, J_post, h_post, a, B)
+        lps[v_new] += ml_new
+        lps[v_new] += v_new * np.log(rho[n]) + (1 - v_new) * np.log(1 - rho[n])
+        v_smpl = sample_discrete_from_log_u(lps, us[step])
+        a[n] = v_smpl
+        if trace is not None:
+            trace.append((int(n), lps[0], lps[1], int(v_smpl)))
+        if v_smpl != v_prev:
+            ml_prev = ml_new
+    return a
+
+
+def sample_gaussian_info(J, h, z):
+    """pybasicbayes.util.stats.sample_gaussian(J=, h=) with z injected (regression.py:334).
+    Third-party restatement, SURVEY Appendix B.2."""
+    L = np.linalg.cholesky(J)
+    x = scipy.linalg.solve_triangular(L, z, lower=True, trans='T')
+    return x + scipy.linalg.cho_solve((L, True), h)
+
+
+def resample_W(J_post, h_post, a, B, z):
+    """regression.py:323-340.  z has one entry per ACTIVE coordinate (|a| B + 1).
+    Returns (W (N,B), b (1,))."""
+    N = len(a)
+    m = _mask(a, B)
+    Jp = J_post[np.ix_(m, m)]
+    hp = h_post[m]
+    Wv = sample_gaussian_info(Jp, hp, z)
+    W = np.zeros((N, B))
+    W[np.asarray(a, dtype=bool), :] = Wv[:-1].reshape((-1, B))
+    return W, np.reshape(Wv[-1], (1,))
+
+
+def deterministic_sparsity(rho):
+    """regression.py:153-155."""
+    return np.all((rho < 1e-6) | (rho > 1 - 1e-6))
+
+
+def resample_regression(X, y, a, W, b, hyper, omega, perm, us, z_full):
+    """One regression.resample (regression.py:265-280) for ONE dataset with all randomness
+    injected: omega (T,), perm (N,), us (N,), z_full (N*B+1,).  z_full is indexed by
+    COORDINATE: the standard normal for active coordinate d is z_full[d] (the CUDA kernel keys
+    its normals by coordinate the same way), i.e. sample_gaussian receives z_full[mask].
+    hyper = dict(rho, mu_w, S_w, mu_b, S_b) in expanded shapes."""
+    N, B = W.shape
+    Xf = flatten_X(X, N, B)
+    J_prior, h_prior = prior_sufficient_statistics(hyper['mu_w'], hyper['S_w'], hyper['mu_b'], hyper['S_b'])
+    J_l, h_l = lkhd_sufficient_statistics(Xf, omega, kappa(y))
+    J_post = J_prior + J_l
+    h_post = h_prior + h_l
+    rho = hyper['rho']
+    if deterministic_sparsity(rho):
+        a_new = np.round(rho).astype(bool)
+    else:
+        a_new = collapsed_resample_a(J_prior, h_prior, J_post, h_post, a, rho, B, perm, us)
+    m = _mask(a_new, B)
+    W_new, b_new = resample_W(J_post, h_post, a_new, B, z_full[m])
+    return a_new, W_new, b_new
+
+
+# --------------------------------------------------------------------------- NIW network (host step)
+def sample_invwishart(S, nu, rng):
+    """pybasicbayes.util.stats.sample_invwishart; third-party restatement (Appendix B.3)."""
+    n = S.shape[0]
+    chol = np.linalg.cholesky(S)
+    if (nu <= 81 + n) and (nu == np.round(nu)):
+        x = rng.standard_normal((int(nu), n))
+    else:
+        x = np.diag(np.sqrt(np.atleast_1d(rng.chisquare(nu - np.arange(n)))))
+        x[np.triu_indices_from(x, 1)] = rng.standard_normal(n * (n - 1) // 2)
+    R = np.linalg.qr(x, 'r')
+    T = scipy.linalg.solve_triangular(R.T, chol.T, lower=True).T
+    return np.dot(T, T.T)
+
+
+def niw_posterior(data, mu_0, sigma_0, kappa_0, nu_0):
+    """NIW posterior hyper-parameters for rows of `data` (n,B); n == 0 -> prior.  Appendix B.3."""
+    D = len(mu_0)
+    data = np.asarray(data).reshape((-1, D))
+    n = data.shape[0]
+    if n == 0:
+        return mu_0, sigma_0, kappa_0, nu_0
+    xbar = data.mean(0)
+    c = data - xbar
+    sumsq = c.T.dot(c)
+    mu_n = kappa_0 / (kappa_0 + n) * mu_0 + n / (kappa_0 + n) * xbar
+    sigma_n = sigma_0 + sumsq + kappa_0 * n / (kappa_0 + n) * np.outer(xbar - mu_0, xbar - mu_0)
+    return mu_n, sigma_n, kappa_0 + n, nu_0 + n
+
+
+def niw_resample(data, mu_0, sigma_0, kappa_0, nu_0, rng):
+    mu_n, sigma_n, kappa_n, nu_n = niw_posterior(data, mu_0, sigma_0, kappa_0, nu_0)
+    sigma = sample_invwishart(sigma_n, nu_n, rng)
+    mu = rng.multivariate_normal(mu_n, sigma / kappa_n)
+    return mu, sigma
+
+
+# --------------------------------------------------------------------------- whole-model port
+class OracleSparseBernoulliGLM(object):
+    """Plain numpy port of SparseBernoulliGLM + NIWSparseNetwork following the reference's own
+    control flow (models.py:166-171,224-236; regression.py:265-280; networks.py:132-149), used for
+    (a) long CPU chains in the distributional tests and (b) the timed CPU baseline in bench.py.
+    Dense dgemm Gram with the XO temporary and 2 Choleskys per flip, exactly like the reference.
+    Randomness: numpy Generator for everything but PG, which uses oracle/pg_devroye.c."""
+
+    def __init__(self, N, basis, rho=0.5, mu_w=0.0, S_w=1.0, mu_b=0.0, S_b=1.0, seed=0,
+                 pg_threads=0):
+        self.N = N
+        self.basis = basis
+        self.B = B = basis.shape[1]
+        self.rng = np.random.default_rng(seed)
+        self.seed = seed
+        self.pg_calls = 0
+        self.pg_threads = pg_threads
+        self.hyper = []
+        for _ in range(N):
+            self.hyper.append(dict(rho=expand_scalar(rho, (N,)), mu_w=expand_scalar(mu_w, (N, B)),
+                                   S_w=expand_cov(S_w, (N, B, B)), mu_b=expand_scalar(mu_b, (1,)),
+                                   S_b=expand_cov(S_b, (1, 1))))
+        # prior draw of the state (regression.py:87-92)
+        self.A = np.zeros((N, N), dtype=bool)
+        self.W = np.zeros((N, N, B))
+        self.bias = np.zeros(N)
+        for n in range(N):
+            h = self.hyper[n]
+            self.A[n] = self.rng.random(N) < h['rho']
+            for m in range(N):
+                self.W[n, m] = self.A[n, m] * self.rng.multivariate_normal(h['mu_w'][m], h['S_w'][m])
+            self.bias[n] = self.rng.multivariate_normal(h['mu_b'], h['S_b'])[0]
+        # NIW network state (networks.py:81-94): off-diagonal and self priors
+        self.niw = dict(mu_0=np.zeros(B), sigma_0=np.eye(B), kappa_0=1.0, nu_0=3.0)
+        self.net_rho = 0.5 * np.ones((N, N))
+        self.data_list = []
+
+    def add_data(self, Y, X=None):
+        if X is None:
+            X = convolve_with_basis(Y, self.basis)
+        self.data_list.append((X, Y))
+
+    def log_likelihood(self):
+        return sum(model_log_likelihood(X, Y, self.A, self.W, self.bias) for X, Y in self.data_list)
+
+    def resample_regression(self, n):
+        """regression.py:265-280 for postsynaptic neuron n."""
+        N, B = self.N, self.B
+        h = self.hyper[n]
+        J_prior, h_prior = prior_sufficient_statistics(h['mu_w'], h['S_w'], h['mu_b'], h['S_b'])
+        J_l = np.zeros_like(J_prior)
+        h_l = np.zeros_like(h_prior)
+        for X, Y in self.data_list:
+            Xf = flatten_X(X, N, B)
+            y = Y[:, n]
+            psi = activation(Xf, self.A[n], self.W[n], self.bias[n:n + 1])
+            self.pg_calls += 1
+            omega = pg1_draw(psi, self.seed, self.pg_calls, rng_kind=1, nthreads=self.pg_threads)
+            Jd, hd = lkhd_sufficient_statistics(Xf, omega, kappa(y))
+            J_l += Jd
+            h_l += hd
+        J_post = J_prior + J_l
+        h_post = h_prior + h_l
+        if deterministic_sparsity(h['rho']):
+            a = np.round(h['rho']).astype(bool)
+        else:
+            perm = self.rng.permutation(N)
+            us = self.rng.random(N)
+            a = collapsed_resample_a(J_prior, h_prior, J_post, h_post, self.A[n], h['rho'], B, perm, us)
+        m = _mask(a, B)
+        z = self.rng.standard_normal(int(m.sum()))
+        Wn, bn = resample_W(J_post, h_post, a, B, z)
+        self.A[n], self.W[n], self.bias[n] = a, Wn, bn[0]
+
+    def resample_network(self):
+        """models.py:228-236 + networks.py:132-149 (NIWSparseNetwork, diagonal special)."""
+        N, B = self.N, self.B
+        off = ~np.eye(N, dtype=bool)
+        p = self.niw
+        mu_o, sig_o = niw_resample(self.W[off & self.A], p['mu_0'], p['sigma_0'], p['kappa_0'],
+                                   max(p['nu_0'], B + 2.), self.rng)
+        mu_s, sig_s = niw_resample(self.W[np.eye(N, dtype=bool) & self.A], p['mu_0'], p['sigma_0'],
+                                   p['kappa_0'], p['nu_0'], self.rng)
+        for n in range(N):
+            mu_w = np.tile(mu_o, (N, 1))
+            S_w = np.tile(sig_o, (N, 1, 1))
+            mu_w[n] = mu_s
+            S_w[n] = sig_s
+            self.hyper[n]['mu_w'] = mu_w
+            self.hyper[n]['S_w'] = S_w
+            self.hyper[n]['rho'] = self.net_rho[n]
+
+    def resample_model(self, neurons=None):
+        for n in (range(self.N) if neurons is None else neurons):
+            self.resample_regression(n)
+        self.resample_network()
