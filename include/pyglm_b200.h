@@ -1,0 +1,87 @@
+/*
+ * pyglm_b200 -- C ABI of the B200-native Gibbs hot path for PyGLM's sparse Bernoulli network GLM.
+ *
+ * The reference (slinderman/pyglm) has no FFI of its own: its boundary is the Python class API
+ * (pyglm/models.py, pyglm/regression.py) and its only native call is pypolyagamma.pgdrawvpar.
+ * Each entry point below states which reference code it stands for (paths relative to the reference
+ * repository).  INTEGRATION.md shows the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; pyglm_last_error() returns the message
+ *     (thread-local);
+ *   - every pointer is a DEVICE pointer owned by the caller unless marked [host]; nothing is allocated,
+ *     freed or synchronised inside; work is enqueued on the caller's stream;
+ *   - all arithmetic is IEEE float64; matrices are row-major; `ld*` are row pitches in elements;
+ *   - padded layouts:  Xp  (T x ldx)   design matrix, columns [0,N*B) = X (n-major, b-minor), column N*B = 1,
+ *                                       the rest 0; ldx = N*B+1 rounded up to a multiple of 32;
+ *                      Wt  (ldx x ldn) Wt[d, j] = coefficient d of local neuron j (row N*B = bias), zero padded;
+ *                      psi, omega (T x ldn); ldn = n_local rounded up to a multiple of 64;
+ *                      J   (n_local x ldx x ldx), lower triangle valid; h (n_local x ldx).
+ */
+#ifndef PYGLM_B200_H
+#define PYGLM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pyglm_stream_t; /* == cudaStream_t */
+
+/* library */
+const char* pyglm_last_error(void);
+int pyglm_abi_version(void);
+int pyglm_device_check(void); /* 0 iff the current device is sm_100 */
+
+/* (1) X = Y * basis.  pyglm/utils/basis.py:5-34 (convolve_with_basis); writes the padded layout Xp. */
+int pyglm_filter_spikes(const double* S, const double* basis, int T, int N, int L, int B, int clip,
+                        double* Xp, int ldx, pyglm_stream_t stream);
+/* user-supplied regressors (models.py:76-77, add_data(data, X=...)): dense (T x NB) <-> padded */
+int pyglm_pack_design(const double* X, int T, int NB, double* Xp, int ldx, pyglm_stream_t stream);
+int pyglm_unpack_design(const double* Xp, int T, int NB, int ldx, double* X, pyglm_stream_t stream);
+
+/* (5) psi = X.vec(a o W) + b for n neurons at once.  pyglm/regression.py:195-201 (activation). */
+int pyglm_activation(const double* Xp, int ldx, const double* Wt, int ldw, int T, int D, int n,
+                     double* psi, int ldpsi, pyglm_stream_t stream);
+/* sum_{t,j} y psi - log(1+e^psi).  pyglm/regression.py:491-494 summed as in models.py:82-96.
+ * workspace: ceil(T/128) * ceil(n/8) doubles.  ll: one double. */
+int pyglm_loglik(const double* Xp, int ldx, const double* Wt, int ldw, int T, int D, int n,
+                 const double* Y, int ldy, int y_col0, double* ll, double* workspace, pyglm_stream_t stream);
+/* logistic(psi).  pyglm/regression.py:524-526 (mean), models.py:153-163 (means). */
+int pyglm_means(const double* Xp, int ldx, const double* Wt, int ldw, int T, int D, int n,
+                double* mu, int ldmu, pyglm_stream_t stream);
+
+/* (2) omega ~ PG(1, psi).  pypolyagamma.pgdrawvpar as called at pyglm/regression.py:501-508. */
+int pyglm_pg_draw(const double* psi, int ldpsi, long long T, int n_valid, double* omega, int ld_out,
+                  unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
+                  pyglm_stream_t stream);
+int pyglm_philox_uniforms(unsigned long long seed, unsigned call_id, unsigned long long elem0, int n_elem,
+                          int count, double* out, pyglm_stream_t stream); /* test hook */
+
+/* (3) J_n = [X,1]^T diag(omega_n) [X,1], lower triangle.  pyglm/regression.py:251-256.
+ * With Om := kappa = y - 1/2 and mode-1 tiles the bias row of the result is h = [X,1]^T kappa (:259-260). */
+int pyglm_gram_tiles(int D, int mode, int* tiles /*[host]*/, int capacity);
+int pyglm_gram_slabs(int ntiles, int n_valid, int T);
+int pyglm_weighted_gram(const double* Xp, int ldx, int T, const double* Om, int ldo, int n_valid,
+                        const int* tiles, int ntiles, int nslabs, double* J, long long stride_n, int ldj,
+                        int i_base, double* workspace, pyglm_stream_t stream);
+
+/* (4) spike-and-slab update of (a, W, b).  pyglm/regression.py:265-340 (_collapsed_resample_a,
+ * _marginal_likelihood, _resample_W) with pybasicbayes' sample_discrete_from_log / sample_gaussian. */
+size_t pyglm_spike_slab_workspace_doubles(int N, int B, int n_loc);
+int pyglm_scan_randomness(int N, int B, int n_loc, int n_off, unsigned long long seed, unsigned call_id,
+                          int* perm, double* us, double* z, int ldz, pyglm_stream_t stream);
+int pyglm_spike_slab_update(int N, int B, int n_loc,
+                            const double* J, long long stride_n, int ldj, const double* h, int ldh,
+                            const double* J0w, const double* h0w, const double* J0b, const double* h0b,
+                            const double* cprior, const double* logit_rho,
+                            const int* perm, const double* us, const double* z, int ldz,
+                            const unsigned char* do_scan, unsigned char* a, double* W, double* bias,
+                            double* P_workspace, double* logodds, double* ml, int* status,
+                            pyglm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYGLM_B200_H */

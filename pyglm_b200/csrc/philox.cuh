@@ -1,0 +1,54 @@
+// Philox4x32-10 counter-based generator and the stream convention shared with the CPU oracle
+// (oracle/pg_devroye.c): key = (seed_lo, seed_hi), counter = (elem_lo, elem_hi, call_id, block#).
+// One independent stream per (seed, call_id, element); a stream hands out 32-bit words four at a
+// time.  Results do not depend on grid shape or on how neurons / time bins are sharded over GPUs.
+#pragma once
+#include <stdint.h>
+
+struct PhiloxStream {
+    uint32_t c0, c1, c2, c3, k0, k1;
+    uint32_t o0, o1, o2, o3;   // scalars, not an array: dynamic indexing would spill to local memory
+    int have;
+
+    __device__ __forceinline__ void seed(uint64_t seed_, uint32_t call_id, uint64_t elem) {
+        k0 = (uint32_t)seed_; k1 = (uint32_t)(seed_ >> 32);
+        c0 = (uint32_t)elem;  c1 = (uint32_t)(elem >> 32);
+        c2 = call_id; c3 = 0; have = 0;
+    }
+    __device__ __forceinline__ void refill() {
+        uint32_t a0 = c0, a1 = c1, a2 = c2, a3 = c3, x0 = k0, x1 = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, a0), lo0 = 0xD2511F53u * a0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, a2), lo1 = 0xCD9E8D57u * a2;
+            uint32_t n0 = hi1 ^ a1 ^ x0, n2 = hi0 ^ a3 ^ x1;
+            a0 = n0; a1 = lo1; a2 = n2; a3 = lo0;
+            x0 += 0x9E3779B9u; x1 += 0xBB67AE85u;
+        }
+        o0 = a0; o1 = a1; o2 = a2; o3 = a3;
+        c3 += 1; have = 4;
+    }
+    __device__ __forceinline__ uint32_t u32() {
+        if (have == 0) refill();
+        uint32_t v = (have == 4) ? o0 : (have == 3) ? o1 : (have == 2) ? o2 : o3;
+        --have;
+        return v;
+    }
+    // uniform on [0,1) from 53 random bits (27 from the first word, 26 from the second)
+    __device__ __forceinline__ double unif() {
+        uint32_t a = u32(), b = u32();
+        return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+    }
+    __device__ __forceinline__ double expon() { return -log1p(-unif()); }
+    // square of a standard normal (Box-Muller, cosine branch)
+    __device__ __forceinline__ double norm_sq() {
+        double u1 = unif(), u2 = unif();
+        double c = cospi(2.0 * u2);   // == cos(2 pi u2) without the large-argument slow path
+        return -2.0 * log1p(-u1) * c * c;
+    }
+    // standard normal (Box-Muller, cosine branch)
+    __device__ __forceinline__ double norm() {
+        double u1 = unif(), u2 = unif();
+        return sqrt(-2.0 * log1p(-u1)) * cospi(2.0 * u2);
+    }
+};

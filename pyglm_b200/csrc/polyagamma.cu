@@ -1,0 +1,138 @@
+// (2) Polya-gamma augmentation: omega[t, j] ~ PG(1, psi[t, j]) for every time bin and local neuron.
+//
+// Replaces pypolyagamma.pgdrawvpar (reference call site regression.py:501-508; third-party C++,
+// not vendored).  Same exact sampler -- Devroye's alternating-series rejection method for J*(1, z)
+// with truncation point t = 0.64 (Polson, Scott & Windle 2013) -- restated for one thread per draw
+// with a private counter-based Philox4x32-10 stream keyed by (seed, call_id, global element index),
+// so draws do not depend on grid shape or on how neurons / time are sharded across GPUs, and match
+// the CPU oracle (oracle/pg_devroye.c, rng_kind 0) element by element.
+// Divergence: the outer loop accepts on its first proposal ~99.9% of the time and the series test
+// ends after one or two terms, so lanes of a warp stay converged except in the rare retry.
+// Algorithmic traffic: 8 B psi read + 8 B omega write per draw (HBM roofline).
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+constexpr double PG_T = 0.64;
+constexpr double PG_T_RECIP = 1.5625;
+constexpr double PG_PI = 3.141592653589793238462643383279502884;
+
+__device__ __forceinline__ double log_pnorm(double x) { return log(0.5 * erfc(-x * 0.70710678118654752440)); }
+
+__device__ __forceinline__ double pg_a(int n, double x) {
+    const double K = (n + 0.5) * PG_PI;
+    if (x > PG_T) return K * exp(-0.5 * K * K * x);
+    if (x > 0.0) {
+        double e = -1.5 * (log(0.5 * PG_PI) + log(x)) + log(K) - 2.0 * (n + 0.5) * (n + 0.5) / x;
+        return exp(e);
+    }
+    return 0.0;
+}
+
+__device__ __forceinline__ double pg_mass_texpon(double z) {
+    const double t = PG_T;
+    double fz = 0.125 * PG_PI * PG_PI + 0.5 * z * z;
+    double b = sqrt(1.0 / t) * (t * z - 1.0);
+    double a = -sqrt(1.0 / t) * (t * z + 1.0);
+    double x0 = log(fz) + fz * t;
+    double xb = x0 - z + log_pnorm(b);
+    double xa = x0 + z + log_pnorm(a);
+    double qdivp = 4.0 / PG_PI * (exp(xb) + exp(xa));
+    return 1.0 / (1.0 + qdivp);
+}
+
+__device__ __forceinline__ double pg_rtigauss(double z, PhiloxStream& r) {
+    const double t = PG_T;
+    double X = t + 1.0;
+    if (PG_T_RECIP > z) {
+        double alpha = 0.0;
+        while (r.unif() > alpha) {
+            double E1 = r.expon(), E2 = r.expon();
+            while (E1 * E1 > 2.0 * E2 / t) { E1 = r.expon(); E2 = r.expon(); }
+            X = 1.0 + E1 * t;
+            X = t / (X * X);
+            alpha = exp(-0.5 * z * z * X);
+        }
+    } else {
+        double mu = 1.0 / z;
+        while (X > t) {
+            double Y = r.norm_sq();
+            double half_mu = 0.5 * mu, mu_Y = mu * Y;
+            X = mu + half_mu * mu_Y - half_mu * sqrt(4.0 * mu_Y + mu_Y * mu_Y);
+            if (r.unif() > mu / (mu + X)) X = mu * mu / X;
+        }
+    }
+    return X;
+}
+
+__device__ double pg1_draw(double psi, PhiloxStream& r) {
+    const double z = fabs(psi) * 0.5;
+    const double fz = 0.125 * PG_PI * PG_PI + 0.5 * z * z;
+    const double mass = pg_mass_texpon(z);
+    for (;;) {
+        double X;
+        if (r.unif() < mass) X = PG_T + r.expon() / fz;
+        else X = pg_rtigauss(z, r);
+        double S = pg_a(0, X);
+        const double Y = r.unif() * S;
+        int n = 0;
+        for (;;) {
+            ++n;
+            if (n & 1) { S -= pg_a(n, X); if (Y <= S) return 0.25 * X; }
+            else       { S += pg_a(n, X); if (Y > S) break; }
+        }
+    }
+}
+
+// grid-stride over the T x n_valid valid entries; element id = (t_off + t) * n_total + (n_off + j)
+__global__ void __launch_bounds__(256)
+pg_draw_kernel(const double* __restrict__ psi, int ldpsi, long long T, int n_valid, int ld_out,
+               unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
+               double* __restrict__ omega) {
+    const long long total = T * (long long)n_valid;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long t = idx / n_valid;
+        const int j = (int)(idx - t * n_valid);
+        PhiloxStream r;
+        r.seed(seed, call_id, (unsigned long long)((t_off + t) * (long long)n_total + n_off + j));
+        omega[t * ld_out + j] = pg1_draw(psi[t * ldpsi + j], r);
+    }
+}
+
+__global__ void philox_unif_kernel(unsigned long long seed, unsigned call_id, unsigned long long elem0, int n_elem,
+                                   int count, double* __restrict__ out) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elem) return;
+    PhiloxStream r;
+    r.seed(seed, call_id, elem0 + e);
+    for (int i = 0; i < count; ++i) out[(size_t)e * count + i] = r.unif();
+}
+
+}  // namespace
+
+// omega[t*ld_out + j] ~ PG(1, psi[t*ldpsi + j]) for t < T, j < n_valid.  Columns j >= n_valid of omega are
+// left untouched (callers keep them zero).  (t_off, n_off, n_total) locate this shard in the global
+// (time x neuron) grid so that the random stream of an element is independent of the sharding.
+extern "C" int pyglm_pg_draw(const double* psi, int ldpsi, long long T, int n_valid, double* omega, int ld_out,
+                             unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
+                             cudaStream_t stream) {
+    PYGLM_CHECK_ARG(psi && omega, "pyglm_pg_draw: null pointer");
+    PYGLM_CHECK_ARG(T > 0 && n_valid > 0 && ldpsi >= n_valid && ld_out >= n_valid && n_total >= n_off + n_valid,
+                    "pyglm_pg_draw: bad shape (T=%lld n=%d ldpsi=%d ld_out=%d n_off=%d n_total=%d)", T, n_valid, ldpsi, ld_out, n_off, n_total);
+    long long total = T * (long long)n_valid;
+    int blocks = (int)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
+    pg_draw_kernel<<<blocks, 256, 0, stream>>>(psi, ldpsi, T, n_valid, ld_out, seed, call_id, t_off, n_off, n_total, omega);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
+// Test hook: out[e*count + i] = i-th uniform of stream (seed, call_id, elem0 + e).
+extern "C" int pyglm_philox_uniforms(unsigned long long seed, unsigned call_id, unsigned long long elem0, int n_elem,
+                                     int count, double* out, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(out && n_elem > 0 && count > 0, "pyglm_philox_uniforms: bad arguments");
+    philox_unif_kernel<<<ceil_div_i(n_elem, 128), 128, 0, stream>>>(seed, call_id, elem0, n_elem, count, out);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}

@@ -1,0 +1,496 @@
+// (4) Spike-and-slab block update of (a_n, W_n, b_n) for every local postsynaptic neuron: one CTA per neuron.
+//
+// Replaces regression.py:265-340: _collapsed_resample_a (:282-320; N sequential flips, each calling
+// _marginal_likelihood :343-378 = two dense Choleskys + two dpotrs of size <= D) and _resample_W (:323-340;
+// sample_gaussian(J=,h=) = Cholesky + triangular solves).
+//
+// Same conditional distributions, different linear algebra.  Let S be the active coordinate set (the B-blocks
+// with a=1 plus the bias).  The kernel keeps P = (Jp_SS)^-1 and mu = P hp_S in compact form and uses the
+// block-bordering identities
+//     add block m:     t = P c,  c = Jp[S,m],  Sm = Jp[m,m] - c^T t,  r = hp[m] - c^T mu
+//                      ml(S+m) - ml(S) = -1/2 log|Sm| + 1/2 r^T Sm^-1 r + prior_m
+//     remove block m:  the same quantity read off P:  +1/2 log|P_mm| + 1/2 mu_m^T P_mm^-1 mu_m + prior_m
+// so one flip costs O(K^2 B) (a mat-vec against P and a rank-B update) instead of O(K^3), and every step is a
+// parallel reduction rather than a sequential factorisation.  The prior J0 is block diagonal
+// (regression.py:218), so its contribution is the closed-form prior_m = 1/2 log|J0_m| - 1/2 h0_m^T J0_m^-1 h0_m.
+// The log-odds of a_m = 1 is  ml(1) - ml(0) + log rho_m - log(1 - rho_m); the flip is decided exactly like
+// sample_discrete_from_log(lps) with uniform u: a_m = (u > p0), p0 = 1 / (1 + exp(logodds)).
+//
+// The Gaussian draw replays the final active set by bordering in ASCENDING coordinate order with the bias
+// last (the order np.ix_(mask, mask) gives the reference): appending block m with Sm = L L^T,
+//     x_m = L^-T z_m,   x_prev -= t x_m,
+// which is, step for step, the back-substitution  x = chol(Jp_SS)^-T z  of sample_gaussian; mu + x is the draw.
+// The same replay accumulates  -1/2 log|Jp_SS| + 1/2 hp^T Jp^-1 hp, i.e. _marginal_likelihood, for parity tests.
+//
+// Randomness (permutation, uniforms, normals) is read from device buffers so tests can inject the reference's
+// own draws; in production those buffers are filled by pyglm_scan_randomness (Philox, below).
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+constexpr int SS_THREADS = 512;
+constexpr int SS_WARPS = SS_THREADS / 32;
+constexpr int SS_BMAX = 16;
+
+struct SpikeSlabArgs {
+    int N, B, D, n_loc;
+    const double* J; long long stride_n; int ldj;     // likelihood J (lower triangle valid), per local neuron
+    const double* h; int ldh;                          // likelihood h
+    const double* J0w;                                 // (n_loc, N, B, B) prior precision blocks
+    const double* h0w;                                 // (n_loc, N, B)
+    const double* J0b; const double* h0b;              // (n_loc,)
+    const double* cprior;                              // (n_loc, N)   1/2 log|J0_m| - 1/2 h0_m^T J0_m^-1 h0_m
+    const double* logit_rho;                           // (n_loc, N)   log rho - log(1 - rho)
+    const int* perm;                                   // (n_loc, N)
+    const double* us;                                  // (n_loc, N)
+    const double* z;                                   // (n_loc, ldz) standard normals keyed by coordinate
+    int ldz;
+    const unsigned char* do_scan;                      // (n_loc,) 0 -> keep a as given (deterministic sparsity)
+    unsigned char* a;                                  // (n_loc, N) in/out
+    double* W;                                         // (n_loc, N, B) out
+    double* bias;                                      // (n_loc,) out
+    double* P;                                         // workspace (n_loc, D, D)
+    double* logodds;                                   // optional (n_loc, N): log-odds per scan step
+    double* ml;                                        // optional (n_loc,): marginal likelihood of the final a
+    int* status;                                       // (n_loc,) 0 ok, 1 = a Schur complement lost positive definiteness
+};
+
+struct Ctx {
+    // problem
+    int N, B, D, NB, ldj, ldp;
+    const double* Jn; const double* hn; const double* J0w; const double* h0w; double J0b, h0b;
+    double* P;
+    // shared state
+    double *mu, *xs, *cb, *tb, *gb, *S, *G, *r, *gr, *xm, *misc;
+    int *cidx, *slot;
+    int K;
+    int tid, lane, warp;
+
+    __device__ __forceinline__ double Jp(int i, int j) const {
+        const int hi = max(i, j), lo = min(i, j);
+        double v = Jn[(size_t)hi * ldj + lo];
+        if (hi < NB) {
+            const int m = hi / B;
+            if (lo / B == m) v += J0w[(size_t)m * B * B + (hi - m * B) * B + (lo - m * B)];
+        } else if (lo == hi) {
+            v += J0b;
+        }
+        return v;
+    }
+    __device__ __forceinline__ double hp(int d) const { return hn[d] + (d < NB ? h0w[d] : h0b); }
+
+    // thread 0: in-place lower Cholesky of the bs x bs matrix in S (row pitch SS_BMAX); returns log|S| or NaN
+    __device__ double chol_small(int bs) {
+        double logdet = 0.0;
+        for (int j = 0; j < bs; ++j) {
+            double d = S[j * SS_BMAX + j];
+            for (int k = 0; k < j; ++k) d -= S[j * SS_BMAX + k] * S[j * SS_BMAX + k];
+            if (!(d > 0.0)) return nan("");
+            const double l = sqrt(d);
+            S[j * SS_BMAX + j] = l;
+            logdet += 2.0 * log(l);
+            for (int i = j + 1; i < bs; ++i) {
+                double s = S[i * SS_BMAX + j];
+                for (int k = 0; k < j; ++k) s -= S[i * SS_BMAX + k] * S[j * SS_BMAX + k];
+                S[i * SS_BMAX + j] = s / l;
+            }
+        }
+        return logdet;
+    }
+    // thread 0: G = (L L^T)^-1 with L in S
+    __device__ void inverse_from_chol(int bs) {
+        for (int c = 0; c < bs; ++c) {
+            double y[SS_BMAX];
+            for (int i = 0; i < bs; ++i) {               // L y = e_c
+                double s = (i == c) ? 1.0 : 0.0;
+                for (int k = 0; k < i; ++k) s -= S[i * SS_BMAX + k] * y[k];
+                y[i] = s / S[i * SS_BMAX + i];
+            }
+            for (int i = bs - 1; i >= 0; --i) {          // L^T g = y
+                double s = y[i];
+                for (int k = i + 1; k < bs; ++k) s -= S[k * SS_BMAX + i] * G[k * SS_BMAX + c];
+                G[i * SS_BMAX + c] = s / S[i * SS_BMAX + i];
+            }
+        }
+    }
+    // thread 0: |L^-1 v|^2
+    __device__ double quad_from_chol(const double* v, int bs) {
+        double y[SS_BMAX], q = 0.0;
+        for (int i = 0; i < bs; ++i) {
+            double s = v[i];
+            for (int k = 0; k < i; ++k) s -= S[i * SS_BMAX + k] * y[k];
+            y[i] = s / S[i * SS_BMAX + i];
+            q += y[i] * y[i];
+        }
+        return q;
+    }
+
+    // Evaluate appending coordinates [coord0, coord0+bs) to the active set.  On return (after the trailing
+    // barrier) thread-0 results sit in shared memory: misc[0] = -1/2 log|Sm| + 1/2 r^T Sm^-1 r (NaN on failure),
+    // S = chol(Sm), G = Sm^-1, r, gr = G r, and xm = L^-T z_m when zc != nullptr.
+    __device__ void eval_add(int coord0, int bs, const double* zc) {
+        for (int e = tid; e < K * bs; e += SS_THREADS) {
+            const int c1 = e / bs, bb = e - c1 * bs;
+            cb[c1 * B + bb] = Jp(cidx[c1], coord0 + bb);
+        }
+        __syncthreads();
+        // t = P c, one warp per row, four right-hand sides per pass
+        for (int c1 = warp; c1 < K; c1 += SS_WARPS) {
+            const double* prow = P + (size_t)c1 * ldp;
+            for (int b0 = 0; b0 < bs; b0 += 4) {
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                for (int c2 = lane; c2 < K; c2 += 32) {
+                    const double p = prow[c2];
+                    const double* cr = cb + c2 * B + b0;
+                    s0 += p * cr[0];
+                    if (b0 + 1 < bs) s1 += p * cr[1];
+                    if (b0 + 2 < bs) s2 += p * cr[2];
+                    if (b0 + 3 < bs) s3 += p * cr[3];
+                }
+                s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+                if (lane == 0) {
+                    tb[c1 * B + b0] = s0;
+                    if (b0 + 1 < bs) tb[c1 * B + b0 + 1] = s1;
+                    if (b0 + 2 < bs) tb[c1 * B + b0 + 2] = s2;
+                    if (b0 + 3 < bs) tb[c1 * B + b0 + 3] = s3;
+                }
+            }
+        }
+        __syncthreads();
+        // Sm = Jp[m,m] - c^T t  and  r = hp[m] - c^T mu : bs*bs + bs dot products of length K
+        for (int p = warp; p < bs * bs + bs; p += SS_WARPS) {
+            double s = 0.0;
+            if (p < bs * bs) {
+                const int bb = p / bs, b2 = p - bb * bs;
+                for (int c1 = lane; c1 < K; c1 += 32) s += cb[c1 * B + bb] * tb[c1 * B + b2];
+                s = warp_sum(s);
+                if (lane == 0) S[bb * SS_BMAX + b2] = Jp(coord0 + bb, coord0 + b2) - s;
+            } else {
+                const int bb = p - bs * bs;
+                for (int c1 = lane; c1 < K; c1 += 32) s += cb[c1 * B + bb] * mu[c1];
+                s = warp_sum(s);
+                if (lane == 0) r[bb] = hp(coord0 + bb) - s;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double logdet = chol_small(bs);
+            if (logdet == logdet) {
+                misc[0] = -0.5 * logdet + 0.5 * quad_from_chol(r, bs);
+                inverse_from_chol(bs);
+                for (int i = 0; i < bs; ++i) {
+                    double s = 0.0;
+                    for (int k = 0; k < bs; ++k) s += G[i * SS_BMAX + k] * r[k];
+                    gr[i] = s;
+                }
+                if (zc) {                                 // xm = L^-T z_m
+                    for (int i = bs - 1; i >= 0; --i) {
+                        double s = zc[coord0 + i];
+                        for (int k = i + 1; k < bs; ++k) s -= S[k * SS_BMAX + i] * xm[k];
+                        xm[i] = s / S[i * SS_BMAX + i];
+                    }
+                }
+            } else {
+                misc[0] = nan("");
+            }
+        }
+        __syncthreads();
+    }
+
+    // Append the block evaluated by the last eval_add.
+    __device__ void commit_add(int coord0, int bs, bool draw) {
+        for (int e = tid; e < K * bs; e += SS_THREADS) {          // gb = t G
+            const int c1 = e / bs, bb = e - c1 * bs;
+            double s = 0.0;
+            for (int k = 0; k < bs; ++k) s += tb[c1 * B + k] * G[k * SS_BMAX + bb];
+            gb[c1 * B + bb] = s;
+        }
+        __syncthreads();
+        for (int c1 = warp; c1 < K; c1 += SS_WARPS) {             // P += gb t^T
+            double* prow = P + (size_t)c1 * ldp;
+            const double* g1 = gb + c1 * B;
+            for (int c2 = lane; c2 < K; c2 += 32) {
+                const double* t2 = tb + c2 * B;
+                double s = 0.0;
+                for (int k = 0; k < bs; ++k) s += g1[k] * t2[k];
+                prow[c2] += s;
+            }
+        }
+        for (int e = tid; e < K * bs; e += SS_THREADS) {          // new border rows / columns
+            const int c1 = e / bs, bb = e - c1 * bs;
+            const double v = -gb[c1 * B + bb];
+            P[(size_t)c1 * ldp + K + bb] = v;
+            P[(size_t)(K + bb) * ldp + c1] = v;
+        }
+        for (int e = tid; e < bs * bs; e += SS_THREADS) {
+            const int bb = e / bs, b2 = e - bb * bs;
+            P[(size_t)(K + bb) * ldp + K + b2] = G[bb * SS_BMAX + b2];
+        }
+        for (int c1 = tid; c1 < K; c1 += SS_THREADS) {
+            double s = 0.0, sx = 0.0;
+            for (int k = 0; k < bs; ++k) { s += gb[c1 * B + k] * r[k]; sx += tb[c1 * B + k] * xm[k]; }
+            mu[c1] -= s;
+            if (draw) xs[c1] -= sx;
+        }
+        if (tid < bs) {
+            mu[K + tid] = gr[tid];
+            if (draw) xs[K + tid] = xm[tid];
+            cidx[K + tid] = coord0 + tid;
+        }
+        __syncthreads();
+        K += bs;
+    }
+
+    // Evaluate removing the B-block stored at compact position pos: misc[0] = ml(with) - ml(without), posterior part.
+    __device__ void eval_remove(int pos) {
+        if (tid == 0) {
+            for (int i = 0; i < B; ++i) {
+                for (int k = 0; k < B; ++k) S[i * SS_BMAX + k] = P[(size_t)(pos + i) * ldp + pos + k];
+                r[i] = mu[pos + i];
+            }
+            const double logdet = chol_small(B);
+            if (logdet == logdet) {
+                misc[0] = 0.5 * logdet + 0.5 * quad_from_chol(r, B);
+                inverse_from_chol(B);                     // G = P_mm^-1
+            } else {
+                misc[0] = nan("");
+            }
+        }
+        __syncthreads();
+    }
+
+    // Remove the block at pos (after eval_remove) and move the last block into its place.
+    __device__ void commit_remove(int pos) {
+        for (int e = tid; e < K * B; e += SS_THREADS) {           // tb = P[:, pos block] (read as rows: P symmetric)
+            const int bb = e / K, c2 = e - bb * K;
+            tb[c2 * B + bb] = P[(size_t)(pos + bb) * ldp + c2];
+        }
+        __syncthreads();
+        for (int e = tid; e < K * B; e += SS_THREADS) {           // gb = tb P_mm^-1
+            const int c1 = e / B, bb = e - c1 * B;
+            double s = 0.0;
+            for (int k = 0; k < B; ++k) s += tb[c1 * B + k] * G[k * SS_BMAX + bb];
+            gb[c1 * B + bb] = s;
+        }
+        __syncthreads();
+        for (int c1 = warp; c1 < K; c1 += SS_WARPS) {             // P -= gb tb^T
+            double* prow = P + (size_t)c1 * ldp;
+            const double* g1 = gb + c1 * B;
+            for (int c2 = lane; c2 < K; c2 += 32) {
+                const double* t2 = tb + c2 * B;
+                double s = 0.0;
+                for (int k = 0; k < B; ++k) s += g1[k] * t2[k];
+                prow[c2] -= s;
+            }
+        }
+        for (int c1 = tid; c1 < K; c1 += SS_THREADS) {            // mu_R -= P_Rm P_mm^-1 mu_m   (r holds mu_m)
+            double s = 0.0;
+            for (int k = 0; k < B; ++k) s += gb[c1 * B + k] * r[k];
+            mu[c1] -= s;
+        }
+        __syncthreads();
+        const int last = K - B;
+        if (pos != last) {
+            for (int e = tid; e < K * B; e += SS_THREADS) {       // rows of the last block -> rows at pos
+                const int bb = e / K, c2 = e - bb * K;
+                P[(size_t)(pos + bb) * ldp + c2] = P[(size_t)(last + bb) * ldp + c2];
+            }
+            __syncthreads();
+            for (int e = tid; e < last * B; e += SS_THREADS) {    // columns of the last block -> columns at pos
+                const int c1 = e / B, bb = e - c1 * B;
+                P[(size_t)c1 * ldp + pos + bb] = P[(size_t)c1 * ldp + last + bb];
+            }
+            if (tid < B) {
+                mu[pos + tid] = mu[last + tid];
+                cidx[pos + tid] = cidx[last + tid];
+            }
+            if (tid == 0) slot[cidx[last] / B] = pos;
+        }
+        __syncthreads();
+        K -= B;
+    }
+};
+
+__global__ void __launch_bounds__(SS_THREADS)
+spike_slab_kernel(SpikeSlabArgs A) {
+    extern __shared__ __align__(16) double ssm[];
+    const int ln = blockIdx.x;
+    const int N = A.N, B = A.B, D = A.D;
+    const int Dpad = (D + 1) & ~1;
+
+    Ctx c;
+    c.N = N; c.B = B; c.D = D; c.NB = N * B; c.ldj = A.ldj; c.ldp = D;
+    c.Jn = A.J + (size_t)ln * A.stride_n;
+    c.hn = A.h + (size_t)ln * A.ldh;
+    c.J0w = A.J0w + (size_t)ln * N * B * B;
+    c.h0w = A.h0w + (size_t)ln * N * B;
+    c.J0b = A.J0b[ln]; c.h0b = A.h0b[ln];
+    c.P = A.P + (size_t)ln * D * D;
+    double* p = ssm;
+    c.mu = p; p += Dpad;
+    c.xs = p; p += Dpad;
+    c.cb = p; p += (size_t)Dpad * B;
+    c.tb = p; p += (size_t)Dpad * B;
+    c.gb = p; p += (size_t)Dpad * B;
+    c.S = p; p += SS_BMAX * SS_BMAX;
+    c.G = p; p += SS_BMAX * SS_BMAX;
+    c.r = p; p += SS_BMAX;
+    c.gr = p; p += SS_BMAX;
+    c.xm = p; p += SS_BMAX;
+    c.misc = p; p += 8;
+    c.cidx = reinterpret_cast<int*>(p);
+    c.slot = c.cidx + Dpad;
+    c.tid = threadIdx.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
+    c.K = 0;
+    const int tid = threadIdx.x;
+
+    unsigned char* a = A.a + (size_t)ln * N;
+    const double* cprior = A.cprior + (size_t)ln * N;
+    const double* lrho = A.logit_rho + (size_t)ln * N;
+    int fail = 0;
+
+    if (tid < SS_BMAX) c.xm[tid] = 0.0;
+    for (int m = tid; m < N; m += SS_THREADS) c.slot[m] = -1;
+    __syncthreads();
+
+    if (A.do_scan[ln]) {
+        // ---- build P, mu for the current active set: bias first, then the active blocks
+        c.eval_add(D - 1, 1, nullptr);
+        if (!(c.misc[0] == c.misc[0])) fail = 1;
+        c.commit_add(D - 1, 1, false);
+        for (int m = 0; m < N && !fail; ++m) {
+            if (!a[m]) continue;
+            if (tid == 0) c.slot[m] = c.K;
+            c.eval_add(m * B, B, nullptr);
+            if (!(c.misc[0] == c.misc[0])) { fail = 1; break; }
+            c.commit_add(m * B, B, false);
+        }
+        // ---- the collapsed scan (regression.py:286-320)
+        const int* perm = A.perm + (size_t)ln * N;
+        const double* us = A.us + (size_t)ln * N;
+        for (int step = 0; step < N && !fail; ++step) {
+            const int m = perm[step];
+            const int pos = c.slot[m];
+            if (pos < 0) c.eval_add(m * B, B, nullptr);
+            else c.eval_remove(pos);
+            const double dpost = c.misc[0];
+            if (!(dpost == dpost)) { fail = 1; break; }
+            const double lo = dpost + cprior[m] + lrho[m];
+            const double p0 = 1.0 / (1.0 + exp(lo));
+            const int v = us[step] > p0;
+            if (A.logodds && tid == 0) A.logodds[(size_t)ln * N + step] = lo;
+            if (pos < 0 && v) {
+                if (tid == 0) { c.slot[m] = c.K; a[m] = 1; }
+                c.commit_add(m * B, B, false);
+            } else if (pos >= 0 && !v) {
+                if (tid == 0) { c.slot[m] = -1; a[m] = 0; }
+                c.commit_remove(pos);
+            } else {
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- Gaussian draw of [W_active; b] by bordering in ascending coordinate order, bias last
+    c.K = 0;
+    double ml = 0.0;
+    const double* zc = A.z + (size_t)ln * A.ldz;
+    for (int m = 0; m <= N && !fail; ++m) {
+        const bool is_bias = (m == N);
+        if (!is_bias && !a[m]) continue;
+        const int coord0 = is_bias ? D - 1 : m * B, bs = is_bias ? 1 : B;
+        c.eval_add(coord0, bs, zc);
+        const double dpost = c.misc[0];
+        if (!(dpost == dpost)) { fail = 1; break; }
+        ml += dpost + (is_bias ? 0.5 * log(c.J0b) - 0.5 * c.h0b * c.h0b / c.J0b : cprior[m]);
+        c.commit_add(coord0, bs, true);
+    }
+    __syncthreads();
+    double* Wn = A.W + (size_t)ln * N * B;
+    for (int e = tid; e < N * B; e += SS_THREADS) Wn[e] = 0.0;
+    __syncthreads();
+    if (!fail) {
+        for (int k = tid; k < c.K; k += SS_THREADS) {
+            const int d = c.cidx[k];
+            const double v = c.mu[k] + c.xs[k];
+            if (d < N * B) Wn[d] = v; else A.bias[ln] = v;
+        }
+    }
+    if (tid == 0) {
+        if (A.ml) A.ml[ln] = fail ? nan("") : ml;
+        A.status[ln] = fail;
+    }
+}
+
+// perm: Fisher-Yates permutation of 0..N-1 per local neuron; us: N uniforms; z: D normals keyed by coordinate.
+// Streams are keyed by the GLOBAL neuron index so that sharding does not change the draws.
+__global__ void scan_randomness_kernel(int N, int D, int n_loc, int n_off, unsigned long long seed, unsigned call_id,
+                                       int* __restrict__ perm, double* __restrict__ us, double* __restrict__ z, int ldz) {
+    const int ln = blockIdx.x;
+    const unsigned long long base = (unsigned long long)(n_off + ln) << 32;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        PhiloxStream r; r.seed(seed, call_id, base + 2ull * i);
+        us[(size_t)ln * N + i] = r.unif();
+    }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        PhiloxStream r; r.seed(seed, call_id, base + 2ull * d + 1ull);
+        z[(size_t)ln * ldz + d] = r.norm();
+    }
+    if (threadIdx.x == 0) {
+        int* pm = perm + (size_t)ln * N;
+        for (int i = 0; i < N; ++i) pm[i] = i;
+        PhiloxStream r; r.seed(seed, call_id, base + 0xFFFFFFFFull);
+        for (int i = N - 1; i > 0; --i) {
+            const int j = (int)(r.unif() * (i + 1));
+            const int tmp = pm[i]; pm[i] = pm[j]; pm[j] = tmp;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" size_t pyglm_spike_slab_workspace_doubles(int N, int B, int n_loc) {
+    const size_t D = (size_t)N * B + 1;
+    return (size_t)n_loc * D * D;
+}
+
+extern "C" int pyglm_scan_randomness(int N, int B, int n_loc, int n_off, unsigned long long seed, unsigned call_id,
+                                     int* perm, double* us, double* z, int ldz, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(perm && us && z && N > 0 && B > 0 && n_loc > 0 && ldz >= N * B + 1, "pyglm_scan_randomness: bad arguments");
+    scan_randomness_kernel<<<n_loc, 256, 0, stream>>>(N, N * B + 1, n_loc, n_off, seed, call_id, perm, us, z, ldz);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
+// One spike-and-slab update of (a, W, b) for n_loc postsynaptic neurons.  See SpikeSlabArgs for shapes.
+extern "C" int pyglm_spike_slab_update(int N, int B, int n_loc,
+                                       const double* J, long long stride_n, int ldj, const double* h, int ldh,
+                                       const double* J0w, const double* h0w, const double* J0b, const double* h0b,
+                                       const double* cprior, const double* logit_rho,
+                                       const int* perm, const double* us, const double* z, int ldz,
+                                       const unsigned char* do_scan, unsigned char* a, double* W, double* bias,
+                                       double* P_workspace, double* logodds, double* ml, int* status,
+                                       cudaStream_t stream) {
+    PYGLM_CHECK_ARG(N > 0 && B > 0 && n_loc > 0, "pyglm_spike_slab_update: N, B, n_loc must be positive");
+    PYGLM_CHECK_ARG(B <= SS_BMAX, "pyglm_spike_slab_update: B=%d exceeds the supported block size %d", B, SS_BMAX);
+    PYGLM_CHECK_ARG(J && h && J0w && h0w && J0b && h0b && cprior && logit_rho && perm && us && z && do_scan && a && W && bias && P_workspace && status,
+                    "pyglm_spike_slab_update: null pointer");
+    const int D = N * B + 1;
+    PYGLM_CHECK_ARG(ldj >= D && ldh >= D && ldz >= D, "pyglm_spike_slab_update: leading dimensions must be >= D=%d", D);
+    SpikeSlabArgs A;
+    A.N = N; A.B = B; A.D = D; A.n_loc = n_loc;
+    A.J = J; A.stride_n = stride_n; A.ldj = ldj; A.h = h; A.ldh = ldh;
+    A.J0w = J0w; A.h0w = h0w; A.J0b = J0b; A.h0b = h0b; A.cprior = cprior; A.logit_rho = logit_rho;
+    A.perm = perm; A.us = us; A.z = z; A.ldz = ldz; A.do_scan = do_scan; A.a = a; A.W = W; A.bias = bias;
+    A.P = P_workspace; A.logodds = logodds; A.ml = ml; A.status = status;
+    const int Dpad = (D + 1) & ~1;
+    size_t smem = ((size_t)2 * Dpad + (size_t)3 * Dpad * B + 2 * SS_BMAX * SS_BMAX + 3 * SS_BMAX + 8) * sizeof(double)
+                + ((size_t)Dpad + N) * sizeof(int);
+    PYGLM_CHECK_ARG(smem <= 227 * 1024, "pyglm_spike_slab_update: N*B=%d too large for the shared-memory state (%zu bytes)", N * B, smem);
+    PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spike_slab_kernel<<<n_loc, SS_THREADS, smem, stream>>>(A);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}

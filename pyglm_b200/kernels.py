@@ -1,0 +1,196 @@
+"""Typed wrappers around the C ABI (include/pyglm_b200.h) operating on torch CUDA tensors.
+
+torch is used only as the owner of device memory and streams; every computation below is one of the
+hand-written sm_100a kernels in pyglm_b200/csrc.  There is no fallback: constructing CudaKernels
+without a B200-class device, or without the built library, raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import cabi
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def pad_ldx(D):
+    """Row pitch of the padded design matrix / J: D = N*B+1 rounded up to a multiple of 32."""
+    return round_up(D, 32)
+
+
+def pad_ldn(n):
+    """Row pitch of psi / omega / Wt: local neuron count rounded up to a multiple of 64."""
+    return round_up(n, 64)
+
+
+class CudaKernels(object):
+    """The compute backend.  One instance per device."""
+
+    name = "cuda-sm100a"
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise cabi.PyglmCudaError("pyglm_b200 needs a CUDA device (B200, sm_100a); none is visible and "
+                                      "there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lib = cabi.load()
+        with torch.cuda.device(self.device):
+            cabi.check(self.lib.pyglm_device_check(), "pyglm_device_check")
+        self.launches = 0          # number of kernel-launching ABI calls made (bench.py reports it)
+        self._tiles = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float64):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def to_device(self, arr, dtype=None):
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=False)
+
+    def _call(self, name, *args, launches=1):
+        with torch.cuda.device(self.device):
+            cabi.call(name, *args)
+        self.launches += launches
+
+    # ------------------------------------------------------------------ (1) filter
+    def filter_spikes(self, S, basis, clip):
+        """S (T,N), basis (L,B) device f64 -> padded design Xp (T, ldx)."""
+        T, N = S.shape
+        L, B = basis.shape
+        ldx = pad_ldx(N * B + 1)
+        Xp = self.empty(T, ldx)
+        self._call("pyglm_filter_spikes", self._p(S), self._p(basis), T, N, L, B, int(bool(clip)),
+                   self._p(Xp), ldx, self._stream(), launches=2)
+        return Xp
+
+    def pack_design(self, X):
+        """dense (T, NB) device f64 -> padded design."""
+        T, NB = X.shape
+        ldx = pad_ldx(NB + 1)
+        Xp = self.empty(T, ldx)
+        self._call("pyglm_pack_design", self._p(X), T, NB, self._p(Xp), ldx, self._stream())
+        return Xp
+
+    def unpack_design(self, Xp, NB):
+        T, ldx = Xp.shape
+        X = self.empty(T, NB)
+        self._call("pyglm_unpack_design", self._p(Xp), T, NB, ldx, self._p(X), self._stream())
+        return X
+
+    # ------------------------------------------------------------------ (5) activation / LL / means
+    def activation(self, Xp, Wt, D, n, out=None):
+        T, ldx = Xp.shape
+        ldn = Wt.shape[1]
+        psi = self.empty(T, ldn) if out is None else out
+        self._call("pyglm_activation", self._p(Xp), ldx, self._p(Wt), ldn, T, D, n, self._p(psi), psi.shape[1],
+                   self._stream())
+        return psi
+
+    def loglik(self, Xp, Wt, D, n, Y, y_col0):
+        T, ldx = Xp.shape
+        ws = self.empty(((T + 127) // 128) * ((n + 7) // 8) + 1)
+        ll = self.empty(1)
+        self._call("pyglm_loglik", self._p(Xp), ldx, self._p(Wt), Wt.shape[1], T, D, n, self._p(Y), Y.shape[1],
+                   y_col0, self._p(ll), self._p(ws), self._stream(), launches=2)
+        return ll
+
+    def means(self, Xp, Wt, D, n):
+        T, ldx = Xp.shape
+        mu = self.empty(T, n)
+        self._call("pyglm_means", self._p(Xp), ldx, self._p(Wt), Wt.shape[1], T, D, n, self._p(mu), n, self._stream())
+        return mu
+
+    # ------------------------------------------------------------------ (2) Polya-gamma
+    def pg_draw(self, psi, n_valid, omega, seed, call_id, t_off, n_off, n_total):
+        T = psi.shape[0]
+        self._call("pyglm_pg_draw", self._p(psi), psi.shape[1], T, n_valid, self._p(omega), omega.shape[1],
+                   seed, call_id, t_off, n_off, n_total, self._stream())
+        return omega
+
+    def philox_uniforms(self, seed, call_id, elem0, n_elem, count):
+        out = self.empty(n_elem, count)
+        self._call("pyglm_philox_uniforms", seed, call_id, elem0, n_elem, count, self._p(out), self._stream())
+        return out
+
+    # ------------------------------------------------------------------ (3) weighted Gram, h
+    def gram_tiles(self, D, mode):
+        key = (D, mode)
+        if key not in self._tiles:
+            n = self.lib.pyglm_gram_tiles(D, mode, None, 0)
+            buf = np.zeros((n, 2), dtype=np.int32)
+            self.lib.pyglm_gram_tiles(D, mode, buf.ctypes.data_as(ctypes.c_void_p), n)
+            self._tiles[key] = self.to_device(buf)
+        return self._tiles[key]
+
+    def weighted_gram(self, Xp, Om, D, n_valid, J=None, nslabs=None):
+        """J[n, i, j] = sum_t Xp[t,i] Xp[t,j] Om[t,n] on the lower triangle (tile granularity)."""
+        T, ldx = Xp.shape
+        tiles = self.gram_tiles(D, 0)
+        if J is None:
+            J = self.zeros(n_valid, ldx, ldx)
+        if nslabs is None:
+            nslabs = self.lib.pyglm_gram_slabs(tiles.shape[0], n_valid, T)
+        ws = self.empty(nslabs * n_valid * ldx * ldx) if nslabs > 1 else None
+        self._call("pyglm_weighted_gram", self._p(Xp), ldx, T, self._p(Om), Om.shape[1], n_valid, self._p(tiles),
+                   tiles.shape[0], nslabs, self._p(J), ldx * ldx, ldx, 0, self._p(ws), self._stream(),
+                   launches=2 if nslabs > 1 else 1)
+        return J
+
+    def xt_kappa(self, Xp, kappa, D, n_valid):
+        """h[n, d] = sum_t Xp[t,d] kappa[t,n]: the bias row of the weighted Gram with weights kappa."""
+        T, ldx = Xp.shape
+        tiles = self.gram_tiles(D, 1)
+        i_base = ((D - 1) // 8) * 8
+        rows = self.zeros(n_valid, 8, ldx)
+        nslabs = self.lib.pyglm_gram_slabs(tiles.shape[0], n_valid, T)
+        ws = self.empty(nslabs * n_valid * 8 * ldx) if nslabs > 1 else None
+        self._call("pyglm_weighted_gram", self._p(Xp), ldx, T, self._p(kappa), kappa.shape[1], n_valid,
+                   self._p(tiles), tiles.shape[0], nslabs, self._p(rows), 8 * ldx, ldx, i_base, self._p(ws),
+                   self._stream(), launches=2 if nslabs > 1 else 1)
+        return rows[:, D - 1 - i_base, :].contiguous()
+
+    # ------------------------------------------------------------------ (4) spike and slab
+    def scan_randomness(self, N, B, n_loc, n_off, seed, call_id):
+        D = N * B + 1
+        perm = self.empty(n_loc, N, dtype=torch.int32)
+        us = self.empty(n_loc, N)
+        z = self.empty(n_loc, D)
+        self._call("pyglm_scan_randomness", N, B, n_loc, n_off, seed, call_id, self._p(perm), self._p(us),
+                   self._p(z), D, self._stream())
+        return perm, us, z
+
+    def spike_slab_update(self, N, B, J, h, prior, perm, us, z, do_scan, a, P_ws=None, want_logodds=False,
+                          want_ml=False):
+        """J (n_loc, ldj, ldj) likelihood Gram (lower triangle), h (n_loc, ldh).  prior: dict of device
+        tensors J0w (n_loc,N,B,B), h0w (n_loc,N,B), J0b, h0b (n_loc,), cprior, logit_rho (n_loc,N).
+        a (n_loc, N) uint8 is updated in place.  Returns (W, bias, logodds|None, ml|None)."""
+        n_loc = a.shape[0]
+        D = N * B + 1
+        if P_ws is None:
+            P_ws = self.empty(n_loc * D * D)
+        W = self.empty(n_loc, N, B)
+        bias = self.empty(n_loc)
+        logodds = self.zeros(n_loc, N) if want_logodds else None
+        ml = self.empty(n_loc) if want_ml else None
+        status = self.zeros(n_loc, dtype=torch.int32)
+        self._call("pyglm_spike_slab_update", N, B, n_loc, self._p(J), J.shape[1] * J.shape[2], J.shape[2],
+                   self._p(h), h.shape[1], self._p(prior["J0w"]), self._p(prior["h0w"]), self._p(prior["J0b"]),
+                   self._p(prior["h0b"]), self._p(prior["cprior"]), self._p(prior["logit_rho"]), self._p(perm),
+                   self._p(us), self._p(z), z.shape[1], self._p(do_scan), self._p(a), self._p(W), self._p(bias),
+                   self._p(P_ws), self._p(logodds), self._p(ml), self._p(status), self._stream())
+        return W, bias, logodds, ml, status

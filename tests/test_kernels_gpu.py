@@ -1,0 +1,349 @@
+"""Kernel-level parity: every CUDA entry point of include/pyglm_b200.h, called through the C ABI, against
+the CPU oracle on the same seeded inputs.  Deterministic pieces: relative tolerance 1e-9 or tighter
+(BASELINE.json north_star: <= 1e-9 in FP64 mode); index work (the a-scan result): exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyglm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def K():
+    from pyglm_b200.kernels import CudaKernels
+    return CudaKernels()
+
+
+def spikes(T, N, seed=0, rate=0.05):
+    return (np.random.default_rng(seed).random((T, N)) < rate).astype(np.float64)
+
+
+def design(K, Y, basis):
+    clip = bool(np.amin(basis) >= 0 and np.amin(Y) >= 0)
+    return K.filter_spikes(K.to_device(Y), K.to_device(basis), clip)
+
+
+def make_Wt(K, A, W, bias, ldx):
+    """host state (n,N), (n,N,B), (n,) -> device Wt (ldx, ldn)"""
+    from pyglm_b200.kernels import pad_ldn
+    n, N, B = W.shape
+    Wt = np.zeros((ldx, pad_ldn(n)))
+    Wt[:N * B, :n] = (A[:, :, None] * W).reshape(n, N * B).T
+    Wt[N * B, :n] = bias
+    return K.to_device(Wt)
+
+
+# ----------------------------------------------------------------------------- RNG
+def test_philox_stream_matches_oracle(K):
+    dev = K.philox_uniforms(12345, 7, 1000, 64, 10).cpu().numpy()
+    for e in (0, 1, 63):
+        np.testing.assert_array_equal(dev[e], O.philox_uniforms(12345, 7, 1000 + e, 10))
+    dev = K.philox_uniforms(2 ** 40 + 3, 2 ** 31 + 5, 2 ** 35, 4, 6).cpu().numpy()
+    np.testing.assert_array_equal(dev[3], O.philox_uniforms(2 ** 40 + 3, 2 ** 31 + 5, 2 ** 35 + 3, 6))
+
+
+# ----------------------------------------------------------------------------- (1) filter
+@pytest.mark.parametrize("T,N,L,B", [(50, 3, 10, 2), (300, 5, 10, 3), (1000, 70, 100, 2), (129, 33, 100, 1),
+                                     (7, 2, 10, 3)])
+def test_filter_matches_oracle(K, T, N, L, B):
+    Y = spikes(T, N, seed=T + N)
+    basis = O.cosine_basis(B, L) / L
+    Xp = design(K, Y, basis).cpu().numpy()
+    X = O.convolve_with_basis(Y, basis).reshape(T, N * B)
+    np.testing.assert_allclose(Xp[:, :N * B], X, rtol=0, atol=1e-14)
+    np.testing.assert_array_equal(Xp[:, N * B], 1.0)
+    np.testing.assert_array_equal(Xp[:, N * B + 1:], 0.0)
+
+
+def test_filter_golden_and_lag_law(K, golden):
+    g = golden("kat_readme.npz")
+    Xp = design(K, g["Y"].astype(float), g["basis"]).cpu().numpy()
+    np.testing.assert_allclose(Xp[:, :4], g["X"].reshape(-1, 4), rtol=0, atol=1e-14)
+    # identity basis: test/test_generate.py:55
+    Y = spikes(1000, 2, seed=5, rate=0.3)
+    X = design(K, Y, np.eye(3)).cpu().numpy()[:, :6].reshape(1000, 2, 3)
+    for n in range(2):
+        for b in range(3):
+            np.testing.assert_array_equal(Y[:-(b + 1), n], X[(b + 1):, n, b])
+
+
+def test_filter_signed_input_not_clipped(K):
+    rng = np.random.default_rng(3)
+    Y = rng.standard_normal((200, 4))
+    basis = rng.standard_normal((10, 2))
+    Xp = design(K, Y, basis).cpu().numpy()
+    np.testing.assert_allclose(Xp[:, :8], O.convolve_direct(Y, basis).reshape(200, 8), rtol=1e-12, atol=1e-13)
+    assert Xp[:, :8].min() < 0
+
+
+def test_pack_unpack_roundtrip(K):
+    X = np.random.default_rng(0).standard_normal((37, 6))
+    Xp = K.pack_design(K.to_device(X))
+    assert Xp.shape[1] == 32
+    np.testing.assert_array_equal(K.unpack_design(Xp, 6).cpu().numpy(), X)
+    np.testing.assert_array_equal(Xp.cpu().numpy()[:, 6], 1.0)
+
+
+# ----------------------------------------------------------------------------- (5) activation / LL / mean
+@pytest.mark.parametrize("T,N,B,n_loc", [(50, 3, 2, 3), (1000, 27, 3, 27), (777, 70, 2, 70), (300, 9, 1, 4)])
+def test_activation_loglik_means(K, T, N, B, n_loc):
+    rng = np.random.default_rng(T)
+    Y = spikes(T, N, seed=1)
+    basis = O.cosine_basis(B, 20) / 20
+    Xp = design(K, Y, basis)
+    X = O.convolve_with_basis(Y, basis)
+    A = rng.random((n_loc, N)) < 0.5
+    W = rng.standard_normal((n_loc, N, B))
+    bias = rng.standard_normal(n_loc) - 2
+    n_off = N - n_loc
+    Wt = make_Wt(K, A, W, bias, Xp.shape[1])
+    D = N * B + 1
+    psi = K.activation(Xp, Wt, D, n_loc).cpu().numpy()
+    ref = np.column_stack([O.activation(X, A[j], W[j], bias[j:j + 1]) for j in range(n_loc)])
+    np.testing.assert_allclose(psi[:, :n_loc], ref, rtol=RTOL, atol=1e-12)
+    assert np.all(psi[:, n_loc:8 * ((n_loc + 7) // 8)] == 0)      # padded neurons inside the written tile
+    ll = float(K.loglik(Xp, Wt, D, n_loc, K.to_device(Y), n_off).cpu()[0])
+    ll_ref = sum(O.log_likelihood_terms(X, Y[:, n_off + j], A[j], W[j], bias[j:j + 1]).sum() for j in range(n_loc))
+    assert ll == pytest.approx(ll_ref, rel=1e-11)
+    mu = K.means(Xp, Wt, D, n_loc).cpu().numpy()
+    np.testing.assert_allclose(mu, O.logistic(ref), rtol=1e-11)
+
+
+def test_loglik_kat_cfg2(K, golden):
+    """SURVEY Appendix D, N=27 B=3 T=1e5: the reference's own LL value for the last neuron."""
+    g = golden("kat_cfg2.npz")
+    N, B, L, T = 27, 3, 100, 100000
+    Y = spikes(T, N, seed=0)
+    Xp = design(K, Y, O.cosine_basis(B, L) / L)
+    assert float(Xp[:, :N * B].sum()) == pytest.approx(float(g["sumX"]), rel=1e-12)
+    np.testing.assert_allclose(Xp[torch.as_tensor(g["X_rows"])].cpu().numpy()[:, :N * B],
+                               g["X_sample"].reshape(-1, N * B), rtol=0, atol=1e-14)
+    Wt = make_Wt(K, g["a"][None], g["W"][None], g["b"], Xp.shape[1])
+    psi = K.activation(Xp, Wt, N * B + 1, 1)
+    assert float(psi[:, 0].sum()) == pytest.approx(float(g["sumpsi"]), rel=1e-10)
+    ll = float(K.loglik(Xp, Wt, N * B + 1, 1, K.to_device(Y), N - 1).cpu()[0])
+    assert ll == pytest.approx(float(g["ll"]), rel=1e-11)
+    # J, h for the same neuron with omega = E[PG]
+    from pyglm_b200.kernels import pad_ldn
+    om = torch.zeros(T, pad_ldn(1), dtype=torch.float64, device=K.device)
+    om[:, 0] = K.to_device(O.pg1_mean(psi[:, 0].cpu().numpy()))
+    J = K.weighted_gram(Xp, om, N * B + 1, 1).cpu().numpy()[0]
+    D = N * B + 1
+    J = np.tril(J[:D, :D])
+    assert np.trace(J) == pytest.approx(float(g["trJ"]), rel=1e-10)
+    assert J[-1, -1] == pytest.approx(float(g["Jcorner"]), rel=1e-10)
+    assert J[1, 0] == pytest.approx(float(g["J10"]), rel=1e-10)
+    Jfull = J + np.tril(J, -1).T
+    assert np.linalg.norm(Jfull) == pytest.approx(float(g["froJ"]), rel=1e-10)
+    kap = torch.zeros(T, pad_ldn(1), dtype=torch.float64, device=K.device)
+    kap[:, 0] = K.to_device(Y[:, N - 1] - 0.5)
+    h = K.xt_kappa(Xp, kap, D, 1).cpu().numpy()[0, :D]
+    assert h.sum() == pytest.approx(float(g["sumh"]), rel=1e-10)
+    assert h[0] == pytest.approx(float(g["h0"]), rel=1e-10)
+
+
+# ----------------------------------------------------------------------------- (2) Polya-gamma
+def test_pg_draws_match_oracle_stream(K):
+    from pyglm_b200.kernels import pad_ldn
+    T, n, n_total, n_off, t_off = 4000, 5, 9, 3, 1000
+    rng = np.random.default_rng(0)
+    psi = np.zeros((T, pad_ldn(n)))
+    psi[:, :n] = rng.standard_normal((T, n)) * 3
+    psi[:10, 0] = [0.0, 1e-9, -1e-9, 30.0, -30.0, 60.0, 100.0, -200.0, 5.0, -5.0]
+    om = K.zeros(T, pad_ldn(n))
+    K.pg_draw(K.to_device(psi), n, om, 99, 4, t_off, n_off, n_total)
+    om = om.cpu().numpy()
+    assert np.all(om[:, n:] == 0)
+    # the oracle draws element e = (t_off+t)*n_total + n_off+j from stream (seed, call_id, e)
+    full = np.zeros(((t_off + T) * n_total,))
+    idx = ((t_off + np.arange(T))[:, None] * n_total + n_off + np.arange(n)[None, :])
+    full[idx.ravel()] = psi[:, :n].ravel()
+    ref = O.pg1_draw(full, 99, 4, rng_kind=0)[idx.ravel()].reshape(T, n)
+    rel = np.abs(om[:, :n] - ref) / ref
+    assert np.all(om[:, :n] > 0)
+    # identical algorithm on an identical stream: libm ulps may flip an accept/reject very rarely
+    assert np.mean(rel > 1e-9) < 1e-4
+    assert np.median(rel) < 1e-14
+
+
+@pytest.mark.parametrize("z", [0.0, 0.5, 2.0, 5.0, 12.0])
+def test_pg_moments(K, z):
+    from pyglm_b200.kernels import pad_ldn
+    T = 400000
+    psi = K.zeros(T, pad_ldn(1))
+    psi[:, 0] = z
+    om = K.zeros(T, pad_ldn(1))
+    K.pg_draw(psi, 1, om, 7, 1, 0, 0, 1)
+    x = om[:, 0].cpu().numpy()
+    m, v = float(O.pg1_mean(np.array(z))), float(O.pg1_var(np.array(z)))
+    assert abs(x.mean() - m) < 5 * np.sqrt(v / T)
+    assert abs(x.var() - v) < 0.02 * v
+
+
+# ----------------------------------------------------------------------------- (3) weighted Gram, h
+@pytest.mark.parametrize("T,N,B,n_loc,nslabs", [(50, 3, 2, 3, None), (2000, 27, 3, 27, None), (2000, 27, 3, 27, 1),
+                                                (3000, 40, 2, 13, 3), (1500, 9, 1, 9, None), (4100, 20, 2, 70, 2)])
+def test_weighted_gram_matches_oracle(K, T, N, B, n_loc, nslabs):
+    from pyglm_b200.kernels import pad_ldn
+    rng = np.random.default_rng(T + N)
+    Y = spikes(T, N, seed=2)
+    basis = O.cosine_basis(B, 20) / 20
+    Xp = design(K, Y, basis)
+    X = O.convolve_with_basis(Y, basis).reshape(T, N * B)
+    D = N * B + 1
+    om = np.zeros((T, pad_ldn(n_loc)))
+    om[:, :n_loc] = rng.random((T, n_loc)) * 0.25
+    kap = np.zeros_like(om)
+    kap[:, :n_loc] = (rng.random((T, n_loc)) < 0.1) - 0.5
+    J = K.weighted_gram(Xp, K.to_device(om), D, n_loc, nslabs=nslabs).cpu().numpy()
+    h = K.xt_kappa(Xp, K.to_device(kap), D, n_loc).cpu().numpy()
+    for j in range(n_loc):
+        Jr, hr = O.lkhd_sufficient_statistics(X, om[:, j], kap[:, j])
+        np.testing.assert_allclose(np.tril(J[j, :D, :D]), np.tril(Jr), rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(h[j, :D], hr, rtol=RTOL, atol=1e-11)
+
+
+# ----------------------------------------------------------------------------- (4) spike and slab
+def prior_tensors(K, hyper_list, N, B):
+    """list (one per local neuron) of dict(rho, mu_w, S_w, mu_b, S_b) -> device prior dict"""
+    from pyglm_b200.priors import prior_arrays
+    arrs = prior_arrays(np.stack([h["rho"] for h in hyper_list]), np.stack([h["mu_w"] for h in hyper_list]),
+                        np.stack([h["S_w"] for h in hyper_list]), np.stack([h["mu_b"][0] for h in hyper_list]),
+                        np.stack([h["S_b"][0, 0] for h in hyper_list]))
+    return {k: K.to_device(v) for k, v in arrs.items() if k != "do_scan"}, arrs["do_scan"]
+
+
+def run_spike_slab(K, N, B, J_l, h_l, hyper_list, a0, perm, us, z):
+    from pyglm_b200.kernels import pad_ldx
+    n_loc = len(hyper_list)
+    D = N * B + 1
+    ldx = pad_ldx(D)
+    Jd = np.zeros((n_loc, ldx, ldx))
+    hd = np.zeros((n_loc, ldx))
+    for j in range(n_loc):
+        Jd[j, :D, :D] = np.tril(J_l[j])          # the kernel must only read the lower triangle
+        Jd[j, :D, :D] += np.triu(np.full((D, D), np.nan), 1)
+        hd[j, :D] = h_l[j]
+    prior, do_scan = prior_tensors(K, hyper_list, N, B)
+    a = K.to_device(np.array(a0, dtype=np.uint8))
+    W, bias, lo, ml, status = K.spike_slab_update(
+        N, B, K.to_device(Jd), K.to_device(hd), prior, K.to_device(np.array(perm, dtype=np.int32)),
+        K.to_device(np.array(us)), K.to_device(np.array(z)), K.to_device(do_scan.astype(np.uint8)), a,
+        want_logodds=True, want_ml=True)
+    assert int(status.abs().sum()) == 0
+    return a.cpu().numpy().astype(bool), W.cpu().numpy(), bias.cpu().numpy(), lo.cpu().numpy(), ml.cpu().numpy()
+
+
+def test_spike_slab_golden_kat_small(K, golden):
+    """The reference's own _collapsed_resample_a + _resample_W on recorded draws (oracle/gen_golden.py)."""
+    for name in ("kat_small.npz", "kat_readme.npz"):
+        g = golden(name)
+        N, B = int(g["N"]), int(g["B"])
+        hyper = dict(rho=0.5 * np.ones(N), mu_w=np.zeros((N, B)), S_w=O.expand_cov(10.0, (N, B, B)),
+                     mu_b=np.array([-2.0]), S_b=np.eye(1))
+        a, W, b, lo, ml = run_spike_slab(K, N, B, [g["J_lkhd"]], [g["h_lkhd"]], [hyper], [g["scan_a0"]],
+                                         [g["scan_perm"]], [g["scan_us"]], [g["draw_z"]])
+        assert np.array_equal(a[0], g["scan_a"])
+        np.testing.assert_allclose(lo[0], g["scan_lps"][:, 1] - g["scan_lps"][:, 0], rtol=1e-8, atol=1e-8)
+        np.testing.assert_allclose(W[0], g["draw_W"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(b, g["draw_b"], rtol=1e-9)
+
+
+def test_marginal_likelihood_kat(K, golden):
+    """_marginal_likelihood (regression.py:343-378) for a fixed a: do_scan = 0 keeps a, ml is reported."""
+    for name in ("kat_small.npz", "kat_readme.npz"):
+        g = golden(name)
+        N, B = int(g["N"]), int(g["B"])
+        hyper = dict(rho=np.where(g["a"], 1.0, 0.0), mu_w=np.zeros((N, B)), S_w=O.expand_cov(10.0, (N, B, B)),
+                     mu_b=np.array([-2.0]), S_b=np.eye(1))
+        z = np.zeros(N * B + 1)
+        a, W, b, lo, ml = run_spike_slab(K, N, B, [g["J_lkhd"]], [g["h_lkhd"]], [hyper], [g["a"]],
+                                         [np.arange(N)], [np.zeros(N)], [z])
+        assert np.array_equal(a[0], g["a"])
+        assert ml[0] == pytest.approx(float(g["ml_a"]), rel=1e-11)
+        hyper["rho"] = np.ones(N)
+        a, W, b, lo, ml = run_spike_slab(K, N, B, [g["J_lkhd"]], [g["h_lkhd"]], [hyper], [np.ones(N)],
+                                         [np.arange(N)], [np.zeros(N)], [z])
+        assert ml[0] == pytest.approx(float(g["ml_ones"]), rel=1e-11)
+        # z = 0 -> the draw is the posterior mean J^-1 h
+        J0, h0 = O.prior_sufficient_statistics(hyper["mu_w"], hyper["S_w"], hyper["mu_b"], hyper["S_b"])
+        mean = np.linalg.solve(J0 + g["J_lkhd"], h0 + g["h_lkhd"])
+        np.testing.assert_allclose(np.concatenate([W[0].ravel(), b]), mean, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,B,T,n_loc,seed", [(6, 2, 400, 6, 0), (27, 3, 3000, 5, 1), (40, 1, 2000, 7, 2),
+                                              (12, 4, 1500, 3, 3)])
+def test_spike_slab_random_vs_oracle(K, N, B, T, n_loc, seed):
+    """Random problems: full regression.resample (a-scan + W draw) vs the oracle on injected draws, with
+    neuron-specific, non-isotropic priors as the NIW network step produces them (models.py:232-236)."""
+    rng = np.random.default_rng(seed)
+    Y = spikes(T, N, seed=seed, rate=0.1)
+    X = O.convolve_with_basis(Y, O.cosine_basis(B, 20) / 20).reshape(T, N * B)
+    hypers, Js, hs, a0s, perms, uss, zs = [], [], [], [], [], [], []
+    for j in range(n_loc):
+        Sw = np.zeros((N, B, B))
+        for m in range(N):
+            M = rng.standard_normal((B, B))
+            Sw[m] = M @ M.T + 0.5 * np.eye(B)
+        hypers.append(dict(rho=rng.uniform(0.1, 0.9, N), mu_w=rng.standard_normal((N, B)), S_w=Sw,
+                           mu_b=rng.standard_normal(1), S_b=np.array([[rng.uniform(0.5, 2)]])))
+        om = rng.random(T) * 0.25
+        Jl, hl = O.lkhd_sufficient_statistics(X, om, Y[:, j] - 0.5)
+        Js.append(Jl)
+        hs.append(hl)
+        a0s.append(rng.random(N) < 0.5)
+        perms.append(rng.permutation(N))
+        uss.append(rng.random(N))
+        zs.append(rng.standard_normal(N * B + 1))
+    a, W, b, lo, ml = run_spike_slab(K, N, B, Js, hs, hypers, a0s, perms, uss, zs)
+    for j in range(n_loc):
+        hy = hypers[j]
+        J0, h0 = O.prior_sufficient_statistics(hy["mu_w"], hy["S_w"], hy["mu_b"], hy["S_b"])
+        trace = []
+        a_ref = O.collapsed_resample_a(J0, h0, J0 + Js[j], h0 + hs[j], a0s[j], hy["rho"], B, perms[j], uss[j],
+                                       trace=trace)
+        lo_ref = np.array([t[2] - t[1] for t in trace])
+        np.testing.assert_allclose(lo[j], lo_ref, rtol=1e-8, atol=1e-8)
+        assert np.array_equal(a[j], a_ref)
+        m = O._mask(a_ref, B)
+        W_ref, b_ref = O.resample_W(J0 + Js[j], h0 + hs[j], a_ref, B, zs[j][m])
+        np.testing.assert_allclose(W[j], W_ref, rtol=1e-8, atol=1e-10)
+        assert b[j] == pytest.approx(b_ref[0], rel=1e-8)
+        assert ml[j] == pytest.approx(O.marginal_likelihood(J0, h0, J0 + Js[j], h0 + hs[j], a_ref, B), rel=1e-10)
+
+
+def test_spike_slab_all_inactive_and_deterministic(K):
+    """Appendix C.9: a may be all False (1x1 bias system); deterministic sparsity (regression.py:274-275)."""
+    N, B, T = 5, 2, 300
+    rng = np.random.default_rng(0)
+    Y = spikes(T, N, seed=4, rate=0.1)
+    X = O.convolve_with_basis(Y, O.cosine_basis(B, 10) / 10).reshape(T, N * B)
+    Jl, hl = O.lkhd_sufficient_statistics(X, rng.random(T) * 0.25, Y[:, 0] - 0.5)
+    z = rng.standard_normal(N * B + 1)
+    for rho in (np.zeros(N), np.ones(N), np.array([1., 0, 0, 1, 0])):
+        hy = dict(rho=rho, mu_w=np.zeros((N, B)), S_w=O.expand_cov(1.0, (N, B, B)), mu_b=np.zeros(1), S_b=np.eye(1))
+        a_det = np.round(rho).astype(bool)
+        a, W, b, lo, ml = run_spike_slab(K, N, B, [Jl], [hl], [hy], [a_det], [np.arange(N)], [np.zeros(N)], [z])
+        J0, h0 = O.prior_sufficient_statistics(hy["mu_w"], hy["S_w"], hy["mu_b"], hy["S_b"])
+        W_ref, b_ref = O.resample_W(J0 + Jl, h0 + hl, a_det, B, z[O._mask(a_det, B)])
+        assert np.array_equal(a[0], a_det)
+        np.testing.assert_allclose(W[0], W_ref, rtol=1e-9, atol=1e-12)
+        assert b[0] == pytest.approx(b_ref[0], rel=1e-9)
+
+
+def test_scan_randomness_is_a_permutation_and_shard_invariant(K):
+    N, B = 37, 2
+    perm, us, z = K.scan_randomness(N, B, 6, 0, 5, 11)
+    p = perm.cpu().numpy()
+    for j in range(6):
+        assert sorted(p[j]) == list(range(N))
+    assert len({tuple(r) for r in p}) == 6
+    perm2, us2, z2 = K.scan_randomness(N, B, 2, 3, 5, 11)      # neurons 3,4 as a separate shard
+    assert torch.equal(perm2, perm[3:5]) and torch.equal(us2, us[3:5]) and torch.equal(z2, z[3:5])
+    u = us.cpu().numpy()
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.1
+    assert abs(float(z.mean())) < 0.2 and abs(float(z.std()) - 1) < 0.2
