@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the Gibbs hot path: sweeps/sec of SparseBernoulliGLM.resample_model().
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3|cfg2|cfg1] [--impl reference]
+
+A "step" is one Gibbs sweep (psi -> PG -> weighted Gram -> spike-and-slab update of all neurons -> host network
+step) over one synthetic recording.  Default workload = BASELINE.json's metric config: N=200, B=2, L=100, T=1e5
+(configs[2], "cfg3"), which fits one B200; with --gpus N the N=200 neurons are sharded over N ranks (strong
+scaling: total work fixed), X replicated, one NCCL all-gather of (a, W, b) per sweep.
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream around exactly K sweeps, barrier +
+synchronize on both sides, max over ranks.  `value` uses device-resident data and a device-only timed region of
+the sweep kernels; `e2e` times the public API call resample_model() with host state in/out every sweep.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "cfg1": dict(N=4, B=1, L=100, T=10000),
+    "cfg2": dict(N=27, B=3, L=100, T=100000),
+    "cfg3": dict(N=200, B=2, L=100, T=100000),
+}
+
+
+def synthetic_spikes(T, N, seed=0):
+    """Y = (default_rng(seed).random((T,N)) < 0.05)."""
+    return (np.random.default_rng(seed).random((T, N)) < 0.05).astype(np.float64)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), source="measured")
+    return dict(hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.reasons, self.proc = index, [], set(), None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append((float(parts[0]), float(parts[1])))
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        self.proc.terminate()
+        sm = sorted(s[0] for s in self.samples)
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None),
+                    sm_max_mhz=(self.samples[0][1] if self.samples else None), reasons=sorted(self.reasons))
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, cfg, name):
+    """The reference's CPU path (numpy/OpenBLAS + OpenMP Devroye PG) as restated by the oracle port, timed on the
+    host cores.  Each step is a BOUNDED SAMPLE of the sweep: `sample_neurons` of the N postsynaptic regressions
+    (each does the full T-length psi / PG / dgemm Gram / 2N-Cholesky a-scan of regression.py:265-280), scaled to
+    a whole sweep by N / sample_neurons -- the regressions are independent and identically sized."""
+    from oracle import pyglm_oracle as O
+    N, B, L, T = cfg["N"], cfg["B"], cfg["L"], cfg["T"]
+    cores = os.cpu_count() or 1
+    basis = O.cosine_basis(B, L) / L
+    Y = synthetic_spikes(T, N)
+    X = O.convolve_with_basis(Y, basis)
+    m = O.OracleSparseBernoulliGLM(N, basis, S_w=10.0, mu_b=-2.0, seed=0, pg_threads=cores)
+    m.add_data(Y, X=X)
+    sample = min(N, args.ref_neurons)
+    neurons = list(range(sample))
+    for _ in range(args.warmup if args.warmup is not None else 1):
+        m.resample_model(neurons=neurons[:1])
+    steps = args.steps if args.steps is not None else 2
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.resample_model(neurons=neurons)
+    dt = (time.perf_counter() - t0) / steps
+    sweep_s = dt * N / sample
+    val = 1.0 / sweep_s
+    desc = "%d of %d regressions per step at full T=%d, scaled by N/%d" % (sample, N, T, sample)
+    line = dict(metric="gibbs_sweeps_per_sec", value=val, unit="sweeps/s", n_gpus=0, steps=steps,
+                warmup=args.warmup if args.warmup is not None else 1, ms_per_step=sweep_s * 1e3,
+                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                impl="reference", config=dict(workload=name, **cfg),
+                cpu_baseline=dict(value=val, unit="sweeps/s", cores=cores, kind="port", sample=desc),
+                e2e=dict(value=val, unit="sweeps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-neurons", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-neurons", type=int, default=1)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    name = "%s: SparseBernoulliGLM N=%d B=%d L=%d T=%d" % (args.config, cfg["N"], cfg["B"], cfg["L"], cfg["T"])
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, cfg, name)
+        return
+
+    import torch
+    import torch.distributed as dist
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from pyglm_b200.models import SparseBernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+
+    steps = args.steps if args.steps is not None else 10
+    warmup = max(3, args.warmup if args.warmup is not None else 3)
+    N, B, L, T = cfg["N"], cfg["B"], cfg["L"], cfg["T"]
+    np.random.seed(0)
+    basis = cosine_basis(B=B, L=L) / L
+    Y = synthetic_spikes(T, N)
+    model = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.), seed=1234)
+    model.add_data(Y, host_X=False)
+    eng = model.engine
+    K = eng.K
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- e2e: the public API, host state in / out every sweep -------------------------------------------
+    for _ in range(warmup):
+        model.resample_model()
+    barrier()
+    h2d0, d2h0, l0 = eng.h2d_bytes, eng.d2h_bytes, K.launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        model.resample_model()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1) / steps
+    h2d = (eng.h2d_bytes - h2d0) // steps
+    d2h = (eng.d2h_bytes - d2h0) // steps
+    launches = K.launches - l0
+
+    # ---- device-resident timing of the sweep's kernels, per kernel, on the launching stream --------------
+    ds = model._device_datasets()[0]
+    A, W, b = model._host_state()
+    n_loc = eng.psi_hi - eng.psi_lo
+    D = eng.D
+    Wt = eng.build_Wt(A, W, b, eng.psi_lo, eng.psi_hi)
+    psi = eng._buf(ds, "psi", (ds.T, Wt.shape[1]))
+    omega = eng._buf(ds, "omega", (ds.T, Wt.shape[1]), zero=True)
+    J = eng._wsbuf("J", (n_loc, eng.ldx, eng.ldx), zero=True)
+    names = ["activation", "pg_draw", "weighted_gram"]
+    evs = {nm: [] for nm in names}
+
+    def timed(nm, fn):
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        c.record()
+        evs[nm].append((a, c))
+
+    for _ in range(2):
+        K.activation(ds.Xp, Wt, D, n_loc, out=psi)
+        K.pg_draw(psi, n_loc, omega, 1, 1, 0, eng.psi_lo, N)
+        K.weighted_gram(ds.Xp, omega, D, n_loc, J=J)
+    barrier()
+    for it in range(steps):
+        timed("activation", lambda: K.activation(ds.Xp, Wt, D, n_loc, out=psi))
+        timed("pg_draw", lambda: K.pg_draw(psi, n_loc, omega, 1, 100 + it, 0, eng.psi_lo, N))
+        timed("weighted_gram", lambda: K.weighted_gram(ds.Xp, omega, D, n_loc, J=J))
+    barrier()
+    kern_ms = {nm: float(np.mean([a.elapsed_time(c) for a, c in evs[nm]])) for nm in names}
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- `value`: whole sweeps with inputs resident in HBM (the engine call, host network step included) --
+    hyp = model._stacked_hypers()
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        A, W, b = eng.sweep([ds], A, W, b, hyp)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1) / steps
+
+    t = torch.tensor([e2e_ms, dev_ms] + [kern_ms[nm] for nm in names], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms, dev_ms = float(t[0]), float(t[1])
+    kern_ms = {nm: float(t[2 + i]) for i, nm in enumerate(names)}
+
+    if rank == 0:
+        pk = peaks()
+        Dp = N * B + 1
+        gram_flop = n_loc * T * Dp * (Dp + 1)                 # symmetric minimum, SURVEY 8(d)
+        gram_tflops = gram_flop / (kern_ms["weighted_gram"] * 1e-3) / 1e12
+        pg_bytes = 16.0 * T * n_loc
+        fp64_peak = float(os.environ.get("PYGLM_FP64_PEAK_TFLOPS", "37.0"))
+        line = dict(
+            metric="gibbs_sweeps_per_sec", value=1e3 / dev_ms, unit="sweeps/s", n_gpus=world, steps=steps,
+            warmup=warmup, ms_per_step=dev_ms, higher_is_better=True, scaling="strong", vs_baseline=None,
+            dtype="f64", data="synthetic",
+            config=dict(workload=name, parallelism="neuron-sharded x%d" % world, l2="inputs (X 333 MB + omega 205 MB) exceed the 126 MB L2", **cfg),
+            e2e=dict(value=1e3 / e2e_ms, unit="sweeps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
+            gpu_launches=int(launches),
+            roofline=dict(kernel="weighted_gram (gram_kernel, FP64 DMMA)", bound="tensor", achieved=gram_tflops,
+                          peak=fp64_peak, unit="TFLOP/s", frac=gram_tflops / fp64_peak, traffic=None,
+                          peak_source="FP64 tensor peak: cuBLAS DGEMM measured in profiles/ (MEASURED_PEAKS.json has no FP64 figure)"),
+            kernels_ms=kern_ms,
+            pg_roofline=dict(bound="hbm", achieved=pg_bytes / (kern_ms["pg_draw"] * 1e-3) / 1e9, peak=pk["hbm_gbs"],
+                             unit="GB/s", frac=pg_bytes / (kern_ms["pg_draw"] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                             peak_source=pk["source"]),
+            weighted_gram_tflops=gram_tflops * world,
+            clocks=clocks,
+        )
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg, args.cpu_baseline_neurons)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, sample):
+    """The oracle port of the reference sweep timed on the host cores for `sample` regressions (bounded)."""
+    from oracle import pyglm_oracle as O
+    N, B, L, T = cfg["N"], cfg["B"], cfg["L"], cfg["T"]
+    cores = os.cpu_count() or 1
+    basis = O.cosine_basis(B, L) / L
+    Y = synthetic_spikes(T, N)
+    m = O.OracleSparseBernoulliGLM(N, basis, S_w=10.0, mu_b=-2.0, seed=0, pg_threads=cores)
+    m.add_data(Y, X=O.convolve_with_basis(Y, basis))
+    t0 = time.perf_counter()
+    m.resample_model(neurons=list(range(sample)))
+    dt = time.perf_counter() - t0
+    return dict(value=1.0 / (dt * N / sample), unit="sweeps/s", cores=cores, kind="port",
+                sample="%d of %d regressions of one sweep at full T=%d (numpy/OpenBLAS + OpenMP Devroye PG), "
+                       "scaled by N/%d" % (sample, N, T, sample))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,281 @@
+"""Model container and Gibbs driver: the drop-in surface of pyglm/models.py.
+
+    SparseBernoulliGLM(N, basis=...)   add_data(Y)   generate(T=...)   resample_model()   log_likelihood()
+    weights / adjacency / biases / means / regressions / network / data_list
+
+The public attributes and call signatures are the reference's (models.py:28-236); what changes is where the
+work happens: add_data filters on the GPU, resample_model runs one GibbsEngine.sweep for all N regressions at
+once (the reference loops over them, models.py:169-171), and log_likelihood / means are single fused kernels.
+Extra keyword-only arguments (`seed`, `shard`, `device`) default to reference behaviour.
+"""
+import numpy as np
+
+from . import networks as _networks
+from . import regression as _regression
+
+
+class DeviceDesign(object):
+    """Stand-in for the host copy of X in `data_list` when add_data(..., host_X=False): the (T, N, B) regressors
+    live in HBM only and are copied to the host on demand (np.asarray(x), x[...])."""
+
+    def __init__(self, dataset, N, B):
+        self._ds, self._N, self._B = dataset, N, B
+        self.shape = (dataset.T, N, B)
+        self.ndim = 3
+        self.dtype = np.dtype(np.float64)
+
+    def __array__(self, dtype=None, copy=None):
+        from .engine import default_kernels
+        X = default_kernels().unpack_design(self._ds.Xp, self._N * self._B).cpu().numpy().reshape(self.shape)
+        return X if dtype is None else X.astype(dtype)
+
+    def __getitem__(self, idx):
+        return np.asarray(self)[idx]
+
+
+class NonlinearAutoregressiveModel(object):
+    """The neuroscience "GLM": a nonlinear vector autoregression, one regression per observed dimension
+    (models.py:8-201)."""
+
+    def __init__(self, N, regressions, basis=None, B=10, seed=None, shard="neuron", comm=None):
+        self.N = N
+        assert len(regressions) == N
+        self.regressions = regressions
+        if basis is None:
+            basis = np.eye(B)
+        else:
+            assert basis.ndim == 2
+        self.basis = basis
+        self.B = self.basis.shape[1]
+        self.data_list = []
+        # device side (created lazily so that constructing / inspecting a model needs no GPU)
+        self._seed = int(np.random.randint(2 ** 31 - 1)) if seed is None else int(seed)
+        self._shard = shard
+        self._comm = comm
+        self._engine = None
+        self._dev = {}           # (id(X), id(Y)) -> (X, Y, DeviceDataset): keeps the keys alive
+
+    # ------------------------------------------------------------------ state views (models.py:54-64)
+    @property
+    def weights(self):
+        return np.array([r.W for r in self.regressions])
+
+    @property
+    def adjacency(self):
+        return np.array([r.a for r in self.regressions])
+
+    @property
+    def biases(self):
+        return np.array([r.b for r in self.regressions]).ravel()
+
+    # ------------------------------------------------------------------ device plumbing
+    @property
+    def engine(self):
+        if self._engine is None:
+            from .engine import GibbsEngine
+            self._engine = GibbsEngine(self.N, self.B, seed=self._seed, comm=self._comm, shard=self._shard)
+        return self._engine
+
+    def _time_slab(self, T):
+        eng = self.engine
+        if eng.shard == "time" and eng.comm.world > 1:
+            from .distributed import time_partition
+            return time_partition(T, eng.comm.world, eng.comm.rank)
+        return 0, T
+
+    def _device_dataset(self, X, Y):
+        """Device copy of one data_list entry, uploaded on first use and cached by object identity (users may
+        replace data_list entries, test/test_generate.py:27)."""
+        key = (id(X), id(Y))
+        hit = self._dev.get(key)
+        if hit is not None and hit[0] is X and hit[1] is Y:
+            return hit[2]
+        if isinstance(X, DeviceDesign):
+            ds = X._ds
+        else:
+            lo, hi = self._time_slab(Y.shape[0])
+            Xs = np.reshape(X, (Y.shape[0], -1))[lo:hi]
+            ds = self.engine.make_dataset(Y[lo:hi], X=Xs, t_off=lo, T_global=Y.shape[0])
+        self._dev[key] = (X, Y, ds)
+        return ds
+
+    def _device_datasets(self):
+        live = set()
+        out = []
+        for X, Y in self.data_list:
+            out.append(self._device_dataset(X, Y))
+            live.add((id(X), id(Y)))
+        for key in [k for k in self._dev if k not in live]:
+            del self._dev[key]
+        return out
+
+    def _host_state(self):
+        return self.adjacency, self.weights, self.biases
+
+    # ------------------------------------------------------------------ data (models.py:66-80)
+    def add_data(self, data, X=None, host_X=True):
+        """Append a (T, N) spike matrix.  X (T, N, B) may be supplied; otherwise it is the causal convolution of
+        `data` with the basis, computed on the GPU.  host_X=False keeps X in HBM only (data_list then holds a
+        DeviceDesign handle): use it for recordings whose X should not be mirrored in host RAM."""
+        N, B = self.N, self.B
+        assert isinstance(data, np.ndarray) and data.ndim == 2 and data.shape[1] == self.N
+        T = data.shape[0]
+        if X is None:
+            lo, hi = self._time_slab(T)
+            if host_X and (lo, hi) != (0, T):
+                raise ValueError("time-sharded add_data needs host_X=False (each rank holds only its slab)")
+            if lo > 0:
+                # filter halo: the L bins before the slab (zero history only at the true start)
+                L = self.basis.shape[0]
+                h0 = max(0, lo - L)
+                ds_full = self.engine.make_dataset(data[h0:hi], basis=self.basis, t_off=h0, T_global=T)
+                ds_full.Xp = ds_full.Xp[lo - h0:].contiguous()
+                ds_full.Y = ds_full.Y[lo - h0:].contiguous()
+                ds_full.T, ds_full.t_off = hi - lo, lo
+                ds = ds_full
+            else:
+                ds = self.engine.make_dataset(data[lo:hi], basis=self.basis, t_off=lo, T_global=T)
+            if host_X:
+                X = np.asarray(DeviceDesign(ds, N, B))
+            else:
+                X = DeviceDesign(ds, N, B)
+            self._dev[(id(X), id(data))] = (X, data, ds)
+        else:
+            assert X.shape == (T, N, B)
+        self.data_list.append((X, data))
+
+    # ------------------------------------------------------------------ scoring (models.py:82-96)
+    def log_likelihood(self, datas=None):
+        A, W, b = self._host_state()
+        if datas is None:
+            dsets = self._device_datasets()
+        else:
+            dsets = []
+            for data in datas:
+                if isinstance(data, tuple):
+                    X, Y = data
+                    dsets.append(self._device_dataset(X, Y))
+                else:
+                    dsets.append(self.engine.make_dataset(data, basis=self.basis))
+        return self.engine.log_likelihood(dsets, A, W, b)
+
+    # ------------------------------------------------------------------ simulation (models.py:98-151)
+    def generate(self, keep=True, T=100, verbose=False, intvl=10):
+        """Simulate T time bins forward from the model (sequential in time by construction).
+
+        Host implementation: generate() is outside the per-sweep hot path; the
+        autoregressive recursion y_t ~ Bern(logistic(W x_t + b)), x_t = window of the last L bins projected on
+        the basis, is evaluated exactly as the reference does, with the basis flipped so that row 0 is lag 1."""
+        if T == 0:
+            return np.zeros((0, self.N))
+        assert isinstance(T, int), "Size must be an integer number of time bins"
+        N, basis = self.N, self.basis
+        L, B = basis.shape
+        flipped = np.flipud(basis)
+        assert not np.allclose(flipped, self.basis)
+        Wmat = self.weights.reshape((N, N * B))
+        b = self.biases
+        Y = np.zeros((T + L, N))
+        X = np.zeros((T + L, N, B))
+        for t in range(L, T + L):
+            if verbose and t % intvl == 0:
+                print("Generate t={}".format(t))
+            X[t] = Y[t - L:t].T.dot(flipped)
+            psi = Wmat.dot(X[t].reshape((N * B,))) + b
+            Y[t] = self.regressions[0].rvs(psi=psi)
+        if keep:
+            self.add_data(Y[L:], X=X[L:])
+        return X[L:], Y[L:]
+
+    # ------------------------------------------------------------------ rates (models.py:153-163)
+    @property
+    def means(self):
+        A, W, b = self._host_state()
+        return [self.engine.means(ds, A, W, b) for ds in self._device_datasets()]
+
+    # ------------------------------------------------------------------ Gibbs sampling (models.py:166-171)
+    def resample_model(self):
+        self.resample_regressions()
+
+    def _stacked_hypers(self):
+        regs = self.regressions
+        return dict(rho=np.stack([r.rho for r in regs]), mu_w=np.stack([r.mu_w for r in regs]),
+                    S_w=np.stack([r.S_w for r in regs]), mu_b=np.array([r.mu_b[0] for r in regs]),
+                    S_b=np.array([r.S_b[0, 0] for r in regs]))
+
+    def resample_regressions(self):
+        """All N regressions in one device sweep (they are conditionally independent given the data)."""
+        A, W, b = self._host_state()
+        A, W, b = self.engine.sweep(self._device_datasets(), A, W, b, self._stacked_hypers())
+        for n, reg in enumerate(self.regressions):
+            reg._a = A[n]
+            reg._W = W[n]
+            reg._b = b[n:n + 1]
+
+    # ------------------------------------------------------------------ plotting (models.py:174-201)
+    def plot(self, fig=None, axs=None, handles=None, title=None, figsize=(6, 3), W_lim=3,
+             pltslice=slice(0, 500), N_to_plot=2, data_index=0):
+        from .plotting import plot_glm
+        return plot_glm(self.data_list[data_index][1], self.weights, self.adjacency, self.means[0], fig=fig,
+                        axs=axs, handles=handles, title=title, figsize=figsize, W_lim=W_lim, pltslice=pltslice,
+                        N_to_plot=N_to_plot)
+
+
+class HierarchicalNonlinearAutoregressiveModel(NonlinearAutoregressiveModel):
+    """Network GLM: the regressions' priors are tied together by a network object (models.py:204-236)."""
+
+    def __init__(self, N, network, regressions, basis=None, B=10, **kwargs):
+        super(HierarchicalNonlinearAutoregressiveModel, self).__init__(N, regressions, basis=basis, B=B, **kwargs)
+        self.network = network
+
+    def resample_model(self):
+        super(HierarchicalNonlinearAutoregressiveModel, self).resample_model()
+        self.resample_network()
+
+    def resample_network(self):
+        """Host step (models.py:228-236).  In multi-GPU runs rank 0 draws and broadcasts the (tiny) network
+        state so every rank pushes identical hyper-parameters.  sigma_W / mu_W / rho are built once, not once
+        per neuron as the reference's property accesses do."""
+        net = self.network
+        comm = self.engine.comm if self._engine is not None else None
+        if comm is None or comm.world == 1:
+            net.resample((self.adjacency, self.weights))
+        else:
+            if comm.rank == 0:
+                net.resample((self.adjacency, self.weights))
+            net.set_state(comm.broadcast_object(net.get_state() if comm.rank == 0 else None))
+        sigma_W, mu_W, rho = net.sigma_W, net.mu_W, net.rho
+        for n, reg in enumerate(self.regressions):
+            reg.S_w = sigma_W[n]
+            reg.mu_w = mu_W[n]
+            reg.rho = rho[n]
+
+
+GLM = NonlinearAutoregressiveModel
+NetworkGLM = HierarchicalNonlinearAutoregressiveModel
+
+
+class _DefaultMixin(object):
+    _network_class = None
+    _regression_class = None
+
+    def __init__(self, N, B=10, basis=None, network=None, network_kwargs=None, regressions=None,
+                 regression_kwargs=None, **kwargs):
+        B = B if basis is None else basis.shape[1]
+        if network is None:
+            network_kwargs = dict() if network_kwargs is None else network_kwargs
+            network = self._network_class(N, B, **network_kwargs)
+        if regressions is None:
+            regression_kwargs = dict() if regression_kwargs is None else regression_kwargs
+            regressions = [self._regression_class(N, B, **regression_kwargs) for _ in range(N)]
+        super(_DefaultMixin, self).__init__(N, network, regressions, B=B, basis=basis, **kwargs)
+
+
+class BernoulliGLM(_DefaultMixin, NetworkGLM):
+    _network_class = _networks.NIWDenseNetwork
+    _regression_class = _regression.BernoulliRegression
+
+
+class SparseBernoulliGLM(_DefaultMixin, NetworkGLM):
+    _network_class = _networks.NIWSparseNetwork
+    _regression_class = _regression.SparseBernoulliRegression

@@ -1,0 +1,221 @@
+"""Model-level parity and statistical validation on the GPU, through the public API
+(SparseBernoulliGLM / NonlinearAutoregressiveModel), mirroring the reference's own tests."""
+import numpy as np
+import pytest
+
+from oracle import pyglm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_means_reference_test(golden):
+    """test/test_generate.py:10-29: X returned by generate() equals the convolution computed by add_data(),
+    and the means agree for both."""
+    from pyglm_b200.models import NonlinearAutoregressiveModel
+    from pyglm_b200.regression import SparseBernoulliRegression
+    from pyglm_b200.utils.basis import cosine_basis
+    np.random.seed(0)
+    N, B, L = 2, 3, 10
+    basis = cosine_basis(B, L=L) / L
+    regressions = [SparseBernoulliRegression(N, B, mu_b=-2, S_b=0.1) for n in range(N)]
+    model = NonlinearAutoregressiveModel(N, regressions, basis=basis)
+    X, Y = model.generate(T=1000, keep=False)
+    model.add_data(Y)
+    Xtest = model.data_list[0][0]
+    assert np.allclose(X, Xtest)
+    means = model.means
+    model.data_list[0] = (X, Y)
+    means2 = model.means
+    assert np.allclose(means, means2)
+    np.testing.assert_allclose(means[0], O.model_means(X, model.adjacency, model.weights, model.biases), rtol=1e-10)
+
+
+def test_basis_reference_test():
+    """test/test_generate.py:42-55: identity basis -> X[t, n, b] = Y[t-(b+1), n]."""
+    from pyglm_b200.models import NonlinearAutoregressiveModel
+    from pyglm_b200.regression import SparseBernoulliRegression
+    np.random.seed(1)
+    N, B = 2, 3
+    regressions = [SparseBernoulliRegression(N, B, mu_b=-2, S_b=0.1) for n in range(N)]
+    model = NonlinearAutoregressiveModel(N, regressions, B=B)
+    X, Y = model.generate(T=1000, keep=False)
+    for n in range(N):
+        for b in range(B):
+            assert np.allclose(Y[:-(b + 1), n], X[(b + 1):, n, b])
+    model.add_data(Y)
+    assert np.allclose(model.data_list[0][0], X)
+
+
+def test_golden_model_values(golden):
+    """The reference's own model-level numbers (oracle/gen_golden.py: reference_tests)."""
+    from pyglm_b200.models import NonlinearAutoregressiveModel
+    from pyglm_b200.regression import SparseBernoulliRegression
+    g = golden("reference_tests.npz")
+    N, B = 2, 3
+    np.random.seed(0)
+    regs = [SparseBernoulliRegression(N, B, mu_b=-2, S_b=0.1) for _ in range(N)]
+    for n in range(N):
+        regs[n].a, regs[n].W, regs[n].b = g["tm_A"][n], g["tm_W"][n], g["tm_b"][n:n + 1]
+    model = NonlinearAutoregressiveModel(N, regs, basis=g["tm_basis"])
+    model.add_data(g["tm_Y"].astype(float))
+    np.testing.assert_allclose(model.data_list[0][0], g["tm_X_conv"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(model.means[0], g["tm_means"], rtol=1e-10)
+    assert model.log_likelihood() == pytest.approx(float(g["tm_ll"]), rel=1e-11)
+    # log_likelihood(datas=[bare array]) re-filters (models.py:88-91)
+    assert model.log_likelihood([g["tm_Y"].astype(float)]) == pytest.approx(float(g["tm_ll"]), rel=1e-11)
+
+
+def test_full_sweep_matches_reference_on_injected_randomness(golden):
+    """One resample_regressions() of the reference itself (fixture full_sweep.npz) reproduced through the
+    public API with the same omega / permutation / uniforms / normals."""
+    from pyglm_b200.models import SparseBernoulliGLM
+    g = golden("full_sweep.npz")
+    N, B = int(g["N"]), int(g["B"])
+    np.random.seed(0)
+    m = SparseBernoulliGLM(N, basis=g["basis"], regression_kwargs=dict(S_w=10.0, mu_b=-2., rho=0.3))
+    for n in range(N):
+        m.regressions[n].a, m.regressions[n].W, m.regressions[n].b = g["A0"][n], g["W0"][n], g["b0"][n:n + 1]
+    m.add_data(g["Y"].astype(float))
+    assert m.log_likelihood() == pytest.approx(float(g["ll0"]), rel=1e-11)
+    np.testing.assert_allclose(m.means[0], g["means0"], rtol=1e-10)
+    m.engine.inject = dict(omega=[g["omega"]], perm=g["perm"], us=g["us"], z=g["z"])
+    m.resample_regressions()
+    assert np.array_equal(m.adjacency, g["A1"])
+    np.testing.assert_allclose(m.weights, g["W1"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(m.biases, g["b1"], rtol=1e-8)
+    assert m.log_likelihood() == pytest.approx(float(g["ll1"]), rel=1e-9)
+    np.testing.assert_allclose(m.means[0], g["means1"], rtol=1e-8)
+    # network step + push-down (models.py:228-236): shapes and wiring
+    m.engine.inject = None
+    m.resample_network()
+    assert m.network.mu_W.shape == g["net_mu_W"].shape and m.network.sigma_W.shape == g["net_sigma_W"].shape
+    np.testing.assert_array_equal(m.network.rho, g["net_rho"])
+    assert m.regressions[0].S_w.shape == g["reg0_S_w"].shape
+    np.testing.assert_array_equal(m.regressions[1].S_w[1], m.network.sigma_W[1, 1])
+    np.testing.assert_array_equal(m.regressions[1].mu_w[0], m.network.mu_W[1, 0])
+
+
+def test_api_surface_and_state_views():
+    from pyglm_b200.models import SparseBernoulliGLM, BernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+    np.random.seed(3)
+    N, B, L = 4, 2, 20
+    basis = cosine_basis(B=B, L=L) / L
+    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.))
+    assert m.weights.shape == (N, N, B) and m.adjacency.shape == (N, N) and m.adjacency.dtype == bool
+    assert m.biases.shape == (N,)
+    for n in range(N):                                  # examples/synthetic.py:30-32
+        m.regressions[n].a[n] = True
+        m.regressions[n].W[n, :] = -2.0
+    assert np.all(np.diagonal(m.adjacency)) and np.all(m.weights[np.arange(N), np.arange(N)] == -2.0)
+    X, Y = m.generate(T=500, keep=True)
+    assert X.shape == (500, N, B) and Y.shape == (500, N) and len(m.data_list) == 1
+    assert m.generate(T=0).shape == (0, N)
+    ll0 = m.log_likelihood()
+    assert ll0 == pytest.approx(O.model_log_likelihood(X, Y, m.adjacency, m.weights, m.biases), rel=1e-11)
+    m.resample_model()
+    assert m.adjacency.dtype == bool and m.weights.shape == (N, N, B)
+    assert np.all(m.weights[~m.adjacency] == 0)           # inactive rows zeroed (regression.py:337-338)
+    # a second dataset: statistics accumulate over data_list (regression.py:237-260)
+    m.add_data(Y[:200].copy())
+    assert len(m.data_list) == 2
+    ll2 = m.log_likelihood()
+    ref = O.model_log_likelihood(X, Y, m.adjacency, m.weights, m.biases) + \
+        O.model_log_likelihood(np.asarray(m.data_list[1][0]), Y[:200], m.adjacency, m.weights, m.biases)
+    assert ll2 == pytest.approx(ref, rel=1e-11)
+    m.resample_model()
+    # dense model: rho = 1 -> a stays all True (deterministic sparsity)
+    d = BernoulliGLM(N, basis=basis)
+    d.add_data(Y)
+    d.resample_model()
+    assert d.adjacency.all()
+    # HBM-only regressors
+    m2 = SparseBernoulliGLM(N, basis=basis)
+    m2.add_data(Y, host_X=False)
+    np.testing.assert_allclose(np.asarray(m2.data_list[0][0]), X, atol=1e-14)
+    m2.resample_model()
+
+
+def test_standalone_regression():
+    """examples/bernoulli_regression.py: a single regression fitted on its own."""
+    from pyglm_b200.regression import SparseBernoulliRegression
+    np.random.seed(2)
+    N, B, T = 2, 1, 1000
+    true_reg = SparseBernoulliRegression(N, B)
+    true_reg.a = np.array([True, True])
+    true_reg.W = np.array([[2.0], [-1.5]])
+    X = np.random.randn(T, N * B)
+    y = true_reg.rvs(X=X)
+    np.testing.assert_allclose(true_reg.activation(X), O.activation(X, true_reg.a, true_reg.W, true_reg.b), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(true_reg.log_likelihood((X, y)),
+                               O.log_likelihood_terms(X, y, true_reg.a, true_reg.W, true_reg.b), rtol=1e-10, atol=1e-12)
+    om = true_reg.omega(X, y)
+    assert om.shape == y.shape and np.all(om > 0)
+    test_reg = SparseBernoulliRegression(N, B)
+    test_reg.a = np.bitwise_not(true_reg.a)
+    As, Ws = [], []
+    for _ in range(60):
+        test_reg.resample([(X, y)])
+        As.append(test_reg.a.copy())
+        Ws.append(test_reg.W.copy())
+    assert np.mean(As[20:], axis=0).min() > 0.9
+    np.testing.assert_allclose(np.mean(Ws[20:], axis=0), true_reg.W, atol=0.5)
+
+
+def _simulate(N, B, L, T, seed):
+    from pyglm_b200.models import SparseBernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+    np.random.seed(seed)
+    basis = cosine_basis(B=B, L=L) / L
+    true = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.))
+    for n in range(N):
+        true.regressions[n].a[n] = True
+        true.regressions[n].W[n, :] = -2.0
+    X, Y = true.generate(T=T, keep=True)
+    return basis, true, X, Y
+
+
+def test_chain_matches_oracle_chain_readme_config():
+    """BASELINE configs[0] (README synthetic: N=4, B=1, L=100, T=1e4): the GPU chain and a CPU oracle chain on the
+    same data must agree in the posterior statistics the reference reports (examples/synthetic.py:51-83):
+    log-likelihood plateau, P(A), posterior mean of W and b."""
+    from pyglm_b200.models import SparseBernoulliGLM
+    N, B, L, T = 4, 1, 100, 10000
+    basis, true, X, Y = _simulate(N, B, L, T, seed=0)
+    ll_true = true.log_likelihood()
+    n_sweeps, burn = 150, 50
+
+    def summarize(lls, As, Ws, bs):
+        return np.array(lls[burn:]), np.mean(As[burn:], 0), np.mean(Ws[burn:], 0), np.mean(bs[burn:], 0)
+
+    gpu = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.), seed=5)
+    gpu.add_data(Y)
+    rec = ([], [], [], [])
+    for _ in range(n_sweeps):
+        gpu.resample_model()
+        for r, v in zip(rec, (gpu.log_likelihood(), gpu.adjacency, gpu.weights, gpu.biases)):
+            r.append(np.array(v))
+    g_ll, g_A, g_W, g_b = summarize(*rec)
+
+    cpu = O.OracleSparseBernoulliGLM(N, basis, S_w=10.0, mu_b=-2.0, seed=9)
+    cpu.add_data(Y, X=X)
+    rec = ([], [], [], [])
+    for _ in range(n_sweeps):
+        cpu.resample_model()
+        for r, v in zip(rec, (cpu.log_likelihood(), cpu.A, cpu.W, cpu.bias)):
+            r.append(np.array(v))
+    c_ll, c_A, c_W, c_b = summarize(*rec)
+
+    # both chains plateau at the true model's likelihood (README figure: within ~10-20 nats)
+    assert abs(g_ll.mean() - ll_true) < 25 and abs(c_ll.mean() - ll_true) < 25
+    assert abs(g_ll.mean() - c_ll.mean()) < 4 * (g_ll.std() + c_ll.std()) / np.sqrt(10) + 3
+    # posterior inclusion probabilities agree (two oracle chains with different seeds differ by up to ~0.15);
+    # connections the oracle finds with certainty are found with certainty
+    assert np.max(np.abs(g_A - c_A)) < 0.3
+    sure = c_A > 0.97
+    assert sure.sum() >= 3 and np.all(g_A[sure] > 0.9)
+    assert np.all(g_A[c_A < 0.3] < 0.55)
+    # posterior means of the weights (W is zero where a = 0, so this is E[a o W]) and of the biases agree
+    np.testing.assert_allclose(g_W[..., 0], c_W[..., 0], atol=0.5)
+    np.testing.assert_allclose(g_W[..., 0][sure], c_W[..., 0][sure], atol=0.35)
+    np.testing.assert_allclose(g_b, c_b, atol=0.12)
