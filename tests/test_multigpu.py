@@ -1,0 +1,70 @@
+"""Two-GPU (NCCL) runs of the CUDA path: neuron-sharded and time-sharded sweeps must reproduce the single-GPU
+chain (the Philox streams are keyed by global (time, neuron) indices, so the draws do not depend on sharding).
+Skipped unless at least two GPUs are visible."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _chain(comm, shard, n_sweeps=3):
+    from pyglm_b200.models import SparseBernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+    N, B, L, T = 10, 2, 20, 5000
+    basis = cosine_basis(B, L) / L
+    Y = (np.random.default_rng(3).random((T, N)) < 0.08).astype(np.float64)
+    np.random.seed(0)
+    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=77, comm=comm,
+                           shard=shard)
+    m.add_data(Y, host_X=False)
+    lls = []
+    for _ in range(n_sweeps):
+        m.resample_model()
+        lls.append(m.log_likelihood())
+    return m.adjacency, m.weights, m.biases, np.array(lls)
+
+
+def _worker(rank, world, port, shard, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from pyglm_b200.distributed import Comm
+        A, W, b, lls = _chain(Comm(), shard)
+        if rank == 0:
+            np.savez(out, A=A, W=W, b=b, lls=lls)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shard", ["neuron", "time"])
+def test_two_gpu_chain_matches_single_gpu(tmp_path, shard):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from pyglm_b200.distributed import Comm
+    A0, W0, b0, lls0 = _chain(Comm(), "neuron")
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_worker, args=(2, _free_port(), shard, out), nprocs=2, join=True)
+    g = np.load(out)
+    assert np.array_equal(g["A"], A0)
+    np.testing.assert_allclose(g["W"], W0, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(g["b"], b0, rtol=1e-8)
+    np.testing.assert_allclose(g["lls"], lls0, rtol=1e-9)
