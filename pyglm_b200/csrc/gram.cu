@@ -26,6 +26,7 @@
 // The same kernel yields h = X~^T (y - 1/2) (regression.py:259-260): with omega := kappa the bias ROW of J
 // is exactly h, so pyglm_xt_kappa runs it over the tiles of that one row.
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -44,7 +45,7 @@ struct GramCfg {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 gram_kernel(const double* __restrict__ Xp, int ldx, const double* __restrict__ Om, int ldo, int T, int t_per_slab,
             const int2* __restrict__ tiles, int n_valid, double* __restrict__ J, long long stride_n, int ldj,
             int i_base, long long slab_stride) {
@@ -56,6 +57,8 @@ gram_kernel(const double* __restrict__ Xp, int ldx, const double* __restrict__ O
     const int2 tile = tiles[blockIdx.x];
     const int i0 = tile.x, j0 = tile.y;
     const int n0 = blockIdx.y * 8 * NT;
+    // n-tiles of this neuron block that hold real neurons (CTA-uniform); the last block may be ragged
+    const int ntcount = min(NT, (n_valid - n0 + 7) / 8);
     const int t_begin = blockIdx.z * t_per_slab;
     const int t_end = min(T, t_begin + t_per_slab);
     // m-tiles of this CTA that touch the lower triangle (CTA-uniform): columns j0+8m <= i0+7
@@ -76,12 +79,16 @@ gram_kernel(const double* __restrict__ Xp, int ldx, const double* __restrict__ O
             for (int x = tid; x < GR_KC * Cfg::CH; x += 256) {
                 const int r = x / Cfg::CH, cc = x - r * Cfg::CH;
                 const int t = tc + r;
-                const int ok = (t < t_end) ? 16 : 0;             // rows past the slab end are zero-filled
+                int ok = (t < t_end) ? 16 : 0;                   // rows past the slab end are zero-filled
                 const size_t tr = (size_t)min(t, t_end - 1);
                 const double* src;
                 if (cc < GR_TJ / 2) src = Xp + tr * ldx + j0 + 2 * cc;
                 else if (cc < GR_OFF_W / 2) src = Xp + tr * ldx + i0 + 2 * (cc - GR_TJ / 2);
-                else src = Om + tr * ldo + n0 + 2 * (cc - GR_OFF_W / 2);
+                else {
+                    int col = n0 + 2 * (cc - GR_OFF_W / 2);      // ragged last block: columns past ldo are zero-filled
+                    if (col >= ldo) { col = 0; ok = 0; }
+                    src = Om + tr * ldo + col;
+                }
                 cp_async16(dst + r * Cfg::LD + 2 * cc, src, ok);
             }
         }
@@ -91,10 +98,11 @@ gram_kernel(const double* __restrict__ Xp, int ldx, const double* __restrict__ O
 #pragma unroll
     for (int s = 0; s < GR_STAGES - 1; ++s) load_chunk(s);
 
-    for (int c = 0; c < nchunks; ++c) {
-        cp_async_wait<GR_STAGES - 2>();
-        __syncthreads();
-        load_chunk(c + GR_STAGES - 1);
+    // The hot loop exists twice: CTAs whose neuron block is full and whose tile lies wholly below the diagonal take
+    // the predicate-free copy (runtime predicates around the DMMAs cost ~10% when measured); the ragged last
+    // neuron block and the diagonal tiles take the predicated one.
+    auto consume = [&](auto full_tag, int c) {
+        constexpr bool FULL = decltype(full_tag)::value;
         const double* row = gsm + (size_t)(c % GR_STAGES) * GR_KC * Cfg::LD + q * Cfg::LD;
 #pragma unroll 2
         for (int kk = 0; kk < GR_KC; kk += 4) {
@@ -105,12 +113,22 @@ gram_kernel(const double* __restrict__ Xp, int ldx, const double* __restrict__ O
             for (int m = 0; m < 4; ++m) a[m] = xi * rk[8 * m + g];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                const double b = rk[GR_OFF_W + 8 * j + g];
+                if (FULL || j < ntcount) {
+                    const double b = rk[GR_OFF_W + 8 * j + g];
 #pragma unroll
-                for (int m = 0; m < 4; ++m)
-                    if (m < mcount) dmma884(acc[m][j][0], acc[m][j][1], a[m], b);
+                    for (int m = 0; m < 4; ++m)
+                        if (FULL || m < mcount) dmma884(acc[m][j][0], acc[m][j][1], a[m], b);
+                }
             }
         }
+    };
+    const bool full = (ntcount == NT) && (mcount == 4);
+    for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<GR_STAGES - 2>();
+        __syncthreads();
+        load_chunk(c + GR_STAGES - 1);
+        if (full) consume(std::true_type{}, c);
+        else consume(std::false_type{}, c);
     }
     cp_async_wait<0>();
 
@@ -147,13 +165,12 @@ gram_reduce_kernel(const double* __restrict__ part, int nslabs, long long slab_s
     J[off] = s;
 }
 
+// n-tiles (groups of 8 neurons) per CTA.  At most 5: gram_kernel<5> needs 123 registers, so two CTAs share an
+// SM (16 warps keep the DMMA pipe ~85% busy; ncu profiles/r01); wider tiles fall to one CTA per SM and measure
+// slower.  Blocks are balanced (n8 = 13 -> 5,5,3 handled by the runtime ntcount), so nothing is padded.
 int pick_nt(int n8) {
-    int best = 1, best_pad = 1 << 30;
-    for (int nt = 1; nt <= 8; ++nt) {
-        int pad = ((n8 + nt - 1) / nt) * nt;
-        if (pad <= best_pad) { best_pad = pad; best = nt; }
-    }
-    return best;
+    const int nblocks = (n8 + 4) / 5;
+    return (n8 + nblocks - 1) / nblocks;
 }
 
 template <int NT>
@@ -221,7 +238,7 @@ extern "C" int pyglm_weighted_gram(const double* Xp, int ldx, int T, const doubl
     int rc = PYGLM_ERR_INVALID;
 #define GR_CASE(NTV) \
     case NTV: rc = launch_gram<NTV>(grid, Xp, ldx, Om, ldo, T, t_per_slab, t2, n_valid, out, stride_n, ldj, i_base, slab_stride, stream); break;
-    switch (NT) { GR_CASE(1) GR_CASE(2) GR_CASE(3) GR_CASE(4) GR_CASE(5) GR_CASE(6) GR_CASE(7) GR_CASE(8) }
+    switch (NT) { GR_CASE(1) GR_CASE(2) GR_CASE(3) GR_CASE(4) GR_CASE(5) }
 #undef GR_CASE
     if (rc) return rc;
     if (nslabs > 1) {

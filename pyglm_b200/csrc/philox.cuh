@@ -5,6 +5,21 @@
 #pragma once
 #include <stdint.h>
 
+// one out-of-line copy of the 10-round block function (inlined at every unif() call site it dominated the
+// instruction footprint of the Polya-gamma kernel); operands and result travel in registers
+static __device__ __noinline__ uint4 philox4x32_10_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 struct PhiloxStream {
     uint32_t c0, c1, c2, c3, k0, k1;
     uint32_t o0, o1, o2, o3;   // scalars, not an array: dynamic indexing would spill to local memory
@@ -16,16 +31,8 @@ struct PhiloxStream {
         c2 = call_id; c3 = 0; have = 0;
     }
     __device__ __forceinline__ void refill() {
-        uint32_t a0 = c0, a1 = c1, a2 = c2, a3 = c3, x0 = k0, x1 = k1;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            uint32_t hi0 = __umulhi(0xD2511F53u, a0), lo0 = 0xD2511F53u * a0;
-            uint32_t hi1 = __umulhi(0xCD9E8D57u, a2), lo1 = 0xCD9E8D57u * a2;
-            uint32_t n0 = hi1 ^ a1 ^ x0, n2 = hi0 ^ a3 ^ x1;
-            a0 = n0; a1 = lo1; a2 = n2; a3 = lo0;
-            x0 += 0x9E3779B9u; x1 += 0xBB67AE85u;
-        }
-        o0 = a0; o1 = a1; o2 = a2; o3 = a3;
+        const uint4 o = philox4x32_10_block(c0, c1, c2, c3, k0, k1);
+        o0 = o.x; o1 = o.y; o2 = o.z; o3 = o.w;
         c3 += 1; have = 4;
     }
     __device__ __forceinline__ uint32_t u32() {

@@ -17,32 +17,49 @@ namespace {
 constexpr double PG_T = 0.64;
 constexpr double PG_T_RECIP = 1.5625;
 constexpr double PG_PI = 3.141592653589793238462643383279502884;
+constexpr double PG_LOG_HALF_PI = 0.45158270528945486472619522989488;   // log(pi/2)
 
-__device__ __forceinline__ double log_pnorm(double x) { return log(0.5 * erfc(-x * 0.70710678118654752440)); }
+// One out-of-line copy of each double-precision transcendental.  Inlined at every call site the kernel was
+// ~77 KB of SASS and ncu showed `no_instruction` (instruction-cache miss) as the dominant stall; divergent
+// lanes of a warp sit in different libm bodies, so footprint matters more than call overhead.
+__device__ __noinline__ double d_exp(double x) { return exp(x); }
+__device__ __noinline__ double d_log(double x) { return log(x); }
+__device__ __noinline__ double d_erfc(double x) { return erfc(x); }
 
-__device__ __forceinline__ double pg_a(int n, double x) {
-    const double K = (n + 0.5) * PG_PI;
-    if (x > PG_T) return K * exp(-0.5 * K * K * x);
-    if (x > 0.0) {
-        double e = -1.5 * (log(0.5 * PG_PI) + log(x)) + log(K) - 2.0 * (n + 0.5) * (n + 0.5) / x;
-        return exp(e);
+struct PgRng {
+    PhiloxStream s;
+    __device__ __forceinline__ double unif() { return s.unif(); }
+    // Exp(1): 1 - u is exactly representable, so this equals -log1p(-u) up to the rounding of log
+    __device__ __forceinline__ double expon() { return -d_log(1.0 - s.unif()); }
+    __device__ __forceinline__ double norm_sq() {
+        const double u1 = s.unif(), u2 = s.unif();
+        const double c = cospi(2.0 * u2);
+        return -2.0 * d_log(1.0 - u1) * c * c;
     }
+};
+
+// a_n(x); lx = log(x) is only read when x <= t
+__device__ __forceinline__ double pg_a(int n, double x, double lx) {
+    const double K = (n + 0.5) * PG_PI;
+    if (x > PG_T) return K * d_exp(-0.5 * K * K * x);
+    if (x > 0.0) return d_exp(-1.5 * (PG_LOG_HALF_PI + lx) + d_log(K) - 2.0 * (n + 0.5) * (n + 0.5) / x);
     return 0.0;
 }
 
-__device__ __forceinline__ double pg_mass_texpon(double z) {
-    const double t = PG_T;
-    double fz = 0.125 * PG_PI * PG_PI + 0.5 * z * z;
-    double b = sqrt(1.0 / t) * (t * z - 1.0);
-    double a = -sqrt(1.0 / t) * (t * z + 1.0);
-    double x0 = log(fz) + fz * t;
-    double xb = x0 - z + log_pnorm(b);
-    double xa = x0 + z + log_pnorm(a);
-    double qdivp = 4.0 / PG_PI * (exp(xb) + exp(xa));
+// p/(p+q), the probability of proposing from the exponential tail.  q/p = (4/pi) fz e^{fz t} [e^{-z} Phi(b) +
+// e^{z} Phi(a)] evaluated directly (the oracle's log form guards an overflow that cannot occur for z < 12).
+// For z >= 12 the mass is below 2^-53, the resolution of the uniform it is compared with, and is taken as 0.
+__device__ __forceinline__ double pg_mass_texpon(double z, double fz) {
+    if (z >= 12.0) return 0.0;
+    const double rt = 1.25;                                     // sqrt(1/t)
+    const double b = rt * (PG_T * z - 1.0), a = -rt * (PG_T * z + 1.0);
+    const double phib = 0.5 * d_erfc(-b * 0.70710678118654752440);
+    const double phia = 0.5 * d_erfc(-a * 0.70710678118654752440);
+    const double qdivp = 4.0 / PG_PI * fz * (d_exp(fz * PG_T - z) * phib + d_exp(fz * PG_T + z) * phia);
     return 1.0 / (1.0 + qdivp);
 }
 
-__device__ __forceinline__ double pg_rtigauss(double z, PhiloxStream& r) {
+__device__ __forceinline__ double pg_rtigauss(double z, PgRng& r) {
     const double t = PG_T;
     double X = t + 1.0;
     if (PG_T_RECIP > z) {
@@ -52,13 +69,13 @@ __device__ __forceinline__ double pg_rtigauss(double z, PhiloxStream& r) {
             while (E1 * E1 > 2.0 * E2 / t) { E1 = r.expon(); E2 = r.expon(); }
             X = 1.0 + E1 * t;
             X = t / (X * X);
-            alpha = exp(-0.5 * z * z * X);
+            alpha = d_exp(-0.5 * z * z * X);
         }
     } else {
-        double mu = 1.0 / z;
+        const double mu = 1.0 / z;
         while (X > t) {
-            double Y = r.norm_sq();
-            double half_mu = 0.5 * mu, mu_Y = mu * Y;
+            const double Y = r.norm_sq();
+            const double half_mu = 0.5 * mu, mu_Y = mu * Y;
             X = mu + half_mu * mu_Y - half_mu * sqrt(4.0 * mu_Y + mu_Y * mu_Y);
             if (r.unif() > mu / (mu + X)) X = mu * mu / X;
         }
@@ -66,21 +83,22 @@ __device__ __forceinline__ double pg_rtigauss(double z, PhiloxStream& r) {
     return X;
 }
 
-__device__ double pg1_draw(double psi, PhiloxStream& r) {
+__device__ double pg1_draw(double psi, PgRng& r) {
     const double z = fabs(psi) * 0.5;
     const double fz = 0.125 * PG_PI * PG_PI + 0.5 * z * z;
-    const double mass = pg_mass_texpon(z);
+    const double mass = pg_mass_texpon(z, fz);
     for (;;) {
         double X;
         if (r.unif() < mass) X = PG_T + r.expon() / fz;
         else X = pg_rtigauss(z, r);
-        double S = pg_a(0, X);
+        const double lx = (X <= PG_T) ? d_log(X) : 0.0;
+        double S = pg_a(0, X, lx);
         const double Y = r.unif() * S;
         int n = 0;
         for (;;) {
             ++n;
-            if (n & 1) { S -= pg_a(n, X); if (Y <= S) return 0.25 * X; }
-            else       { S += pg_a(n, X); if (Y > S) break; }
+            if (n & 1) { S -= pg_a(n, X, lx); if (Y <= S) return 0.25 * X; }
+            else       { S += pg_a(n, X, lx); if (Y > S) break; }
         }
     }
 }
@@ -95,8 +113,8 @@ pg_draw_kernel(const double* __restrict__ psi, int ldpsi, long long T, int n_val
          idx += (long long)gridDim.x * blockDim.x) {
         const long long t = idx / n_valid;
         const int j = (int)(idx - t * n_valid);
-        PhiloxStream r;
-        r.seed(seed, call_id, (unsigned long long)((t_off + t) * (long long)n_total + n_off + j));
+        PgRng r;
+        r.s.seed(seed, call_id, (unsigned long long)((t_off + t) * (long long)n_total + n_off + j));
         omega[t * ld_out + j] = pg1_draw(psi[t * ldpsi + j], r);
     }
 }

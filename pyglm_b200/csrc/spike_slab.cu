@@ -140,13 +140,20 @@ struct Ctx {
             const double* prow = P + (size_t)c1 * ldp;
             for (int b0 = 0; b0 < bs; b0 += 4) {
                 double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                for (int c2 = lane; c2 < K; c2 += 32) {
-                    const double p = prow[c2];
-                    const double* cr = cb + c2 * B + b0;
-                    s0 += p * cr[0];
-                    if (b0 + 1 < bs) s1 += p * cr[1];
-                    if (b0 + 2 < bs) s2 += p * cr[2];
-                    if (b0 + 3 < bs) s3 += p * cr[3];
+                for (int c0 = lane; c0 < K; c0 += 128) {
+                    double pv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) pv[u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;   // 4 loads in flight
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c2 = min(c0 + 32 * u, K - 1);
+                        const double p = pv[u];
+                        const double* cr = cb + c2 * B + b0;
+                        s0 += p * cr[0];
+                        if (b0 + 1 < bs) s1 += p * cr[1];
+                        if (b0 + 2 < bs) s2 += p * cr[2];
+                        if (b0 + 3 < bs) s3 += p * cr[3];
+                    }
                 }
                 s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
                 if (lane == 0) {
@@ -210,11 +217,20 @@ struct Ctx {
         for (int c1 = warp; c1 < K; c1 += SS_WARPS) {             // P += gb t^T
             double* prow = P + (size_t)c1 * ldp;
             const double* g1 = gb + c1 * B;
-            for (int c2 = lane; c2 < K; c2 += 32) {
-                const double* t2 = tb + c2 * B;
-                double s = 0.0;
-                for (int k = 0; k < bs; ++k) s += g1[k] * t2[k];
-                prow[c2] += s;
+            for (int c0 = lane; c0 < K; c0 += 128) {
+                double pv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pv[u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c2 = c0 + 32 * u;
+                    if (c2 < K) {
+                        const double* t2 = tb + c2 * B;
+                        double s = 0.0;
+                        for (int k = 0; k < bs; ++k) s += g1[k] * t2[k];
+                        prow[c2] = pv[u] + s;
+                    }
+                }
             }
         }
         for (int e = tid; e < K * bs; e += SS_THREADS) {          // new border rows / columns
@@ -277,11 +293,20 @@ struct Ctx {
         for (int c1 = warp; c1 < K; c1 += SS_WARPS) {             // P -= gb tb^T
             double* prow = P + (size_t)c1 * ldp;
             const double* g1 = gb + c1 * B;
-            for (int c2 = lane; c2 < K; c2 += 32) {
-                const double* t2 = tb + c2 * B;
-                double s = 0.0;
-                for (int k = 0; k < B; ++k) s += g1[k] * t2[k];
-                prow[c2] -= s;
+            for (int c0 = lane; c0 < K; c0 += 128) {
+                double pv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pv[u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c2 = c0 + 32 * u;
+                    if (c2 < K) {
+                        const double* t2 = tb + c2 * B;
+                        double s = 0.0;
+                        for (int k = 0; k < B; ++k) s += g1[k] * t2[k];
+                        prow[c2] = pv[u] - s;
+                    }
+                }
             }
         }
         for (int c1 = tid; c1 < K; c1 += SS_THREADS) {            // mu_R -= P_Rm P_mm^-1 mu_m   (r holds mu_m)
