@@ -42,8 +42,9 @@ def peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), source="measured")
-    return dict(hbm_gbs=6650.0, source="fallback")
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), bf16_burst=d.get("bf16_tflops", 1590.0),
+                    bf16_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
 class ClockSampler(object):
@@ -128,6 +129,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gram", default="auto", choices=["auto", "fp64", "tc"])
+    ap.add_argument("--shard", default="neuron", choices=["neuron", "time"])
     ap.add_argument("--ref-neurons", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-neurons", type=int, default=1)
@@ -157,7 +160,8 @@ def main():
     np.random.seed(0)
     basis = cosine_basis(B=B, L=L) / L
     Y = synthetic_spikes(T, N)
-    model = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.), seed=1234)
+    model = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.), seed=1234,
+                               gram=args.gram, shard=args.shard)
     model.add_data(Y, host_X=False)
     eng = model.engine
     K = eng.K
@@ -186,47 +190,24 @@ def main():
     d2h = (eng.d2h_bytes - d2h0) // steps
     launches = K.launches - l0
 
-    # ---- device-resident timing of the sweep's kernels, per kernel, on the launching stream --------------
+    # ---- `value`: whole sweeps with inputs resident in HBM (the engine call), with every kernel phase timed by
+    # CUDA events on the launching stream inside the same timed region -------------------------------------
     ds = model._device_datasets()[0]
     A, W, b = model._host_state()
     n_loc = eng.psi_hi - eng.psi_lo
-    D = eng.D
-    Wt = eng.build_Wt(A, W, b, eng.psi_lo, eng.psi_hi)
-    psi = eng._buf(ds, "psi", (ds.T, Wt.shape[1]))
-    omega = eng._buf(ds, "omega", (ds.T, Wt.shape[1]), zero=True)
-    J = eng._wsbuf("J", (n_loc, eng.ldx, eng.ldx), zero=True)
-    names = ["activation", "pg_draw", "weighted_gram"]
-    evs = {nm: [] for nm in names}
-
-    def timed(nm, fn):
-        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn()
-        c.record()
-        evs[nm].append((a, c))
-
-    for _ in range(2):
-        K.activation(ds.Xp, Wt, D, n_loc, out=psi)
-        K.pg_draw(psi, n_loc, omega, 1, 1, 0, eng.psi_lo, N)
-        K.weighted_gram(ds.Xp, omega, D, n_loc, J=J)
-    barrier()
-    for it in range(steps):
-        timed("activation", lambda: K.activation(ds.Xp, Wt, D, n_loc, out=psi))
-        timed("pg_draw", lambda: K.pg_draw(psi, n_loc, omega, 1, 100 + it, 0, eng.psi_lo, N))
-        timed("weighted_gram", lambda: K.weighted_gram(ds.Xp, omega, D, n_loc, J=J))
-    barrier()
-    kern_ms = {nm: float(np.mean([a.elapsed_time(c) for a, c in evs[nm]])) for nm in names}
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- `value`: whole sweeps with inputs resident in HBM (the engine call, host network step included) --
     hyp = model._stacked_hypers()
     barrier()
+    eng.profile = {}
     ev0.record()
     for _ in range(steps):
         A, W, b = eng.sweep([ds], A, W, b, hyp)
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1) / steps
+    kern_ms = eng.phase_ms()
+    eng.profile = None
+    clocks = sampler.stop() if rank == 0 else None
+    names = sorted(kern_ms)
 
     t = torch.tensor([e2e_ms, dev_ms] + [kern_ms[nm] for nm in names], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -237,21 +218,40 @@ def main():
     if rank == 0:
         pk = peaks()
         Dp = N * B + 1
-        gram_flop = n_loc * T * Dp * (Dp + 1)                 # symmetric minimum, SURVEY 8(d)
+        T_loc = ds.T
+        gram_flop = n_loc * T_loc * Dp * (Dp + 1)             # symmetric minimum, SURVEY 8(d), per rank
         gram_tflops = gram_flop / (kern_ms["weighted_gram"] * 1e-3) / 1e12
-        pg_bytes = 16.0 * T * n_loc
-        fp64_peak = float(os.environ.get("PYGLM_FP64_PEAK_TFLOPS", "37.0"))
+        pg_bytes = 16.0 * T_loc * n_loc
+        tc = "gram_tc_mma" in kern_ms
+        if tc:
+            # tcgen05 path: S(S+1)/2 int8 digit products per algorithmic MAC (S = 4 -> 10)
+            S = eng.gram_digits
+            ops = gram_flop * (S * (S + 1) // 2)
+            achieved = ops / (kern_ms["gram_tc_mma"] * 1e-3) / 1e12
+            peak = 2.0 * pk["bf16_sustained"]
+            roof = dict(kernel="gram_tc_kernel (tcgen05 kind::i8, %d radix-256 digits, exact int32/int64 sums)" % S,
+                        bound="tensor", achieved=achieved, peak=peak, unit="TOP/s", frac=achieved / peak, traffic=None,
+                        algorithmic="N*T*D*(D+1) FP64 flop x %d int8 digit products" % (S * (S + 1) // 2),
+                        peak_source="2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s): int8 runs on the same "
+                                    "tcgen05 pipe at twice the bf16 rate; kernel timed inside the sweep" % pk["source"])
+        else:
+            fp64_peak = float(os.environ.get("PYGLM_FP64_PEAK_TFLOPS", "35.5"))
+            roof = dict(kernel="gram_kernel (FP64 DMMA)", bound="tensor", achieved=gram_tflops, peak=fp64_peak,
+                        unit="TFLOP/s", frac=gram_tflops / fp64_peak, traffic=None,
+                        peak_source="FP64 tensor peak: cuBLAS DGEMM measured in profiles/r01_fp64_peak.json "
+                                    "(MEASURED_PEAKS.json has no FP64 figure)")
         line = dict(
             metric="gibbs_sweeps_per_sec", value=1e3 / dev_ms, unit="sweeps/s", n_gpus=world, steps=steps,
             warmup=warmup, ms_per_step=dev_ms, higher_is_better=True, scaling="strong", vs_baseline=None,
-            dtype="f64", data="synthetic",
-            config=dict(workload=name, parallelism="neuron-sharded x%d" % world, l2="inputs (X 333 MB + omega 205 MB) exceed the 126 MB L2", **cfg),
+            dtype="f64 (Gram: int8 digits on tcgen05, exact integer sums, <=1e-9 of FP64)" if tc else "f64",
+            data="synthetic",
+            config=dict(workload=name, parallelism="%s-sharded x%d" % (eng.shard, world), gram=("tc" if tc else "fp64"),
+                        l2="inputs (X 333 MB, omega 205 MB, Z digit planes 32 GB) exceed the 126 MB L2", **cfg),
             e2e=dict(value=1e3 / e2e_ms, unit="sweeps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
             gpu_launches=int(launches),
-            roofline=dict(kernel="weighted_gram (gram_kernel, FP64 DMMA)", bound="tensor", achieved=gram_tflops,
-                          peak=fp64_peak, unit="TFLOP/s", frac=gram_tflops / fp64_peak, traffic=None,
-                          peak_source="FP64 tensor peak: cuBLAS DGEMM measured in profiles/ (MEASURED_PEAKS.json has no FP64 figure)"),
+            roofline=roof,
             kernels_ms=kern_ms,
+            dominant_kernel=max((k for k in kern_ms if not k.startswith("gram_tc_")), key=lambda k: kern_ms[k]),
             pg_roofline=dict(bound="hbm", achieved=pg_bytes / (kern_ms["pg_draw"] * 1e-3) / 1e9, peak=pk["hbm_gbs"],
                              unit="GB/s", frac=pg_bytes / (kern_ms["pg_draw"] * 1e-3) / 1e9 / pk["hbm_gbs"],
                              peak_source=pk["source"]),

@@ -67,6 +67,33 @@ int pyglm_weighted_gram(const double* Xp, int ldx, int T, const double* Om, int 
                         const int* tiles, int ntiles, int nslabs, double* J, long long stride_n, int ldj,
                         int i_base, double* workspace, pyglm_stream_t stream);
 
+/* (3') The same weighted Gram (pyglm/regression.py:251-256) on the tcgen05 tensor cores, for non-negative designs:
+ * both operands are split into S radix-256 digits (digit 0 unsigned, the rest signed round-to-nearest), every
+ * digit product of order a+b < S is an exact int8 x int8 -> int32 tcgen05.mma, orders are recombined in int64 and
+ * scaled to FP64 once.  S = 4 agrees with the FP64 kernel to ~1e-10 relative (tests: 1e-9).
+ *   pyglm_gram_tc_geometry   out[8] = {M pairs, Mpad, Tpad, Npad, neurons per tile, neuron tiles, time chunks,
+ *                                      64-byte K blocks per chunk}                                   [host]
+ *   pyglm_column_max         cmax[c] = max_t A[t,c] (A >= 0), *neg_flag = 1 if any entry is negative
+ *   pyglm_gram_tc_build_z    digit planes Zs[S][Mpad][Tpad] of Z[t,(i,j)] = Xp[t,i] Xp[t,j], i >= j, pair index
+ *                            i(i+1)/2 + j; once per dataset (Z does not depend on the Gibbs state); Zs zeroed by caller
+ *   pyglm_gram_tc_slice_omega  per sweep: omax[n] = max_t Om[t,n] and digit planes Os[S][Npad][Tpad]
+ *   pyglm_gram_tc_mma        Jint[n][pair] = sum_t sum_{a+b<S} 256^(S-1-a-b) Zs[a][pair][t] Os[b][n][t]  (exact int64)
+ *   pyglm_gram_tc_finalize   J[n][i][j] = Jint[n][pair] * 2^(ex_i + ex_j + eo_n - 8S - 8), lower triangle        */
+int pyglm_gram_tc_geometry(int D, int n_valid, long long T, int S, long long* out /*[host]*/);
+int pyglm_column_max(const double* A, int ld, long long T, int ncols, double* cmax, int* neg_flag,
+                     pyglm_stream_t stream);
+int pyglm_gram_tc_build_z(const double* Xp, int ldx, long long T, int D, const double* cmax, int S,
+                          unsigned char* Zs, long long Mpad, long long Tpad, pyglm_stream_t stream);
+int pyglm_gram_tc_slice_omega(const double* Om, int ldo, long long T, int n_valid, int S, double* omax,
+                              int* neg_flag, unsigned char* Os, int Npad, long long Tpad, pyglm_stream_t stream);
+int pyglm_gram_tc_mma(const unsigned char* Zs, const unsigned char* Os, int D, int n_valid, long long T, int S,
+                      long long* Jint, long long ldjint, int max_ctas, pyglm_stream_t stream);
+/* measurement hook: the MMA schedule above without operand loads / result atomics (int8 tensor-pipe peak) */
+int pyglm_gram_tc_mma_probe(const unsigned char* Zs, const unsigned char* Os, int D, int n_valid, long long T, int S,
+                            long long* Jint, long long ldjint, pyglm_stream_t stream);
+int pyglm_gram_tc_finalize(const long long* Jint, long long ldjint, const double* cmax, const double* omax,
+                           int D, int n_valid, int S, double* J, long long stride_n, int ldj, pyglm_stream_t stream);
+
 /* (4) spike-and-slab update of (a, W, b).  pyglm/regression.py:265-340 (_collapsed_resample_a,
  * _marginal_likelihood, _resample_W) with pybasicbayes' sample_discrete_from_log / sample_gaussian. */
 size_t pyglm_spike_slab_workspace_doubles(int N, int B, int n_loc);

@@ -482,3 +482,49 @@ class OracleSparseBernoulliGLM(object):
         for n in (range(self.N) if neurons is None else neurons):
             self.resample_regression(n)
         self.resample_network()
+
+
+# --------------------------------------------------------------------------- integer-digit Gram (checker)
+# Restatement of the arithmetic of pyglm_b200/csrc/gram_tc.cu (OUR tensor-core formulation of
+# regression.py:251-256, not a reference function): used by the tests to check the digit planes and the int64
+# sums of the tcgen05 kernel bit for bit.  The FP64 value it approximates is lkhd_sufficient_statistics above.
+def tc_exponent(cmax):
+    """2^e > 1.02 * cmax (0 for an all-zero column)."""
+    import math
+    return 0 if not cmax > 0 else math.frexp(cmax * 1.02)[1]
+
+
+def tc_digits(scaled, S):
+    """S radix-256 digits of rint(scaled): digit 0 (most significant) unsigned, the others signed round-to-nearest."""
+    v = np.rint(scaled).astype(np.int64)
+    out = []
+    for _ in range(S - 1):
+        lo = ((v + 128) & 255) - 128
+        out.append(lo)
+        v = (v - lo) >> 8
+    out.append(v)
+    return out[::-1]
+
+
+def tc_gram_reference(Xt, om, S):
+    """Xt (T, D) = [X, 1] >= 0, om (T, n) > 0.  Returns (Jint (n, D(D+1)/2) int64 exact digit sums,
+    J (n, D, D) float64 lower triangle) as gram_tc.cu computes them."""
+    T, D = Xt.shape
+    n = om.shape[1]
+    ex = [tc_exponent(c) for c in Xt.max(0)]
+    eo = [tc_exponent(c) for c in om.max(0)]
+    od = [tc_digits(om[:, c] * 2.0 ** (8 * S - eo[c]), S) for c in range(n)]
+    Jint = np.zeros((n, D * (D + 1) // 2), dtype=np.int64)
+    J = np.zeros((n, D, D))
+    for i in range(D):
+        for j in range(i + 1):
+            p = i * (i + 1) // 2 + j
+            zd = tc_digits(Xt[:, j] * Xt[:, i] * 2.0 ** (8 * S - ex[i] - ex[j]), S)
+            for c in range(n):
+                tot = 0
+                for a in range(S):
+                    for b in range(S - a):
+                        tot += int(np.dot(zd[a], od[c][b])) << (8 * (S - 1 - a - b))
+                Jint[c, p] = tot
+                J[c, i, j] = float(tot) * 2.0 ** (ex[i] + ex[j] + eo[c] - 8 * S - 8)
+    return Jint, J

@@ -1,0 +1,605 @@
+// (3') Weighted Gram on the 5th-generation tensor cores: J_n = X~^T diag(omega_n) X~ for all local neurons as ONE
+// integer GEMM on tcgen05 (kind::i8, int32 accumulators in TMEM), exact in integer arithmetic and recombined in
+// FP64 -- an error-compensated split of the FP64 contraction of regression.py:251-256 (Ozaki scheme).
+//
+//     J[(i,j), n] = sum_t Z[t,(i,j)] * omega[t,n],      Z[t,(i,j)] = X~[t,i] X~[t,j]   (i >= j)
+//
+// Both operands are written as S radix-256 digits of a fixed-point number with a power-of-two scale per row,
+//     Z[t,p]     ~ 2^(ex_i+ex_j-8S) * sum_s 256^(S-1-s) zs[s][p][t]       (scale: product of column bounds of X~)
+//     omega[t,n] ~ 2^(eo_n-8S)      * sum_s 256^(S-1-s) os[s][n][t]       (scale: column maximum of omega)
+// digit 0 unsigned in [0,255] (all operands are >= 0 on this path), digits 1.. signed round-to-nearest in
+// [-128,127], so the dropped tail is zero-mean.  Every digit product zs[a] * os[b] with a+b <= S-1 is one
+// tcgen05.mma into the int32 accumulator of "order" g = a+b; sums of at most 16384 time bins stay below 2^31, so
+// each accumulator is EXACT, and orders are recombined as int64 (sum_g acc_g << 8(S-1-g)), added across time chunks
+// with integer atomics (order-independent => bitwise deterministic) and scaled to FP64 once at the end.
+// With S=4 the result differs from the FP64 DMMA kernel by ~1e-10 relative (tests state 1e-9).
+//
+// Z does not depend on the Gibbs state: its digits are built once per dataset (pyglm_gram_tc_build_z) and stay
+// resident in HBM (S * D(D+1)/2 * T bytes: 32 GB at N=200, B=2, T=1e5 -- this is what 180 GB of HBM3e is for).
+// The per-sweep kernel is then a pure TMA -> tcgen05 pipeline:
+//   warp 0   TMA producer: per 64-byte K block, S digit tiles of Z (128 pairs x 64 B) and S of omega (NT x 64 B),
+//            SWIZZLE_64B, 3-stage mbarrier ring
+//   warp 1   one lane issues S(S+1)/2 x 2 tcgen05.mma (M=128, N=NT, K=32) per stage; tcgen05.commit frees the stage
+//   warps 2-5 epilogue: tcgen05.ld the S accumulators, combine to int64, red.global.add.u64 into Jint[n][pair]
+// Work item = (pair tile, neuron tile, time chunk <= 16384 bins); persistent CTAs stride over the item list.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TC_BM = 128;          // pairs per tile = UMMA M
+constexpr int TC_BK = 64;           // bytes of K per stage row == swizzle span (SWIZZLE_64B)
+constexpr int TC_UK = 32;           // K of one kind::i8 tcgen05.mma
+constexpr int TC_KCHUNK = 16384;    // max time bins per int32-exact accumulation
+constexpr int TC_THREADS = 192;
+constexpr int TC_STAGES = 3;
+constexpr long long TC_SPIN_LIMIT = 4000000000LL;   // cycles; a wait this long is a hang -> trap
+
+__host__ __device__ inline int tc_nt_max(int S) { return (512 / S) / 16 * 16; }   // TMEM: S accumulators x NT columns
+
+// power-of-two scale exponent: 2^e > 1.02 * cmax  (digit 0 then stays <= 252)
+__host__ __device__ inline int tc_exponent(double cmax) {
+    if (!(cmax > 0.0)) return 0;
+    int e;
+    frexp(cmax * 1.02, &e);
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > TC_SPIN_LIMIT) asm volatile("trap;");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], 8-bit integer operands, int32 accumulation
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, rows of TC_BK bytes, 8-row groups 8*TC_BK bytes apart, hardware swizzle == TC_BK bytes
+// (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_64B and a 64-byte inner box).
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    constexpr uint64_t layout = (TC_BK == 128) ? 2 : (TC_BK == 64) ? 4 : 6;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address / 16
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8 * TC_BK) >> 4) << 32;         // stride byte offset between 8-row groups / 16
+    d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+    d |= layout << 61;                               // swizzle mode
+    return d;
+}
+// kind::i8 instruction descriptor: int32 accumulate, K-major A and B, M=128
+__device__ __forceinline__ uint32_t tc_idesc(int a_signed, int b_signed, int n) {
+    return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+struct TcItems {
+    int n_mtiles, n_ntiles, n_chunks;
+    int blocks_per_chunk;   // TC_BK-byte K blocks per time chunk
+    int n_blocks;           // total K blocks (Tpad / TC_BK)
+    int nt;                 // neurons per tile (multiple of 16, <= tc_nt_max)
+    int n_valid;            // real neurons
+    long long M;            // real pairs
+    long long Mpad;         // rows per digit plane of Z
+    int Npad;               // rows per digit plane of omega
+    long long ldj;          // pitch of Jint rows (>= Mpad)
+    int probe;              // 1: issue-rate probe -- no operand loads, no result atomics (tensor-pipe peak measurement)
+};
+
+template <int S>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapO,
+               long long* __restrict__ Jint, const TcItems it) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    constexpr int A_SLICE = TC_BM * TC_BK;                       // bytes of one Z digit tile
+    const int B_SLICE = it.nt * TC_BK;                           // bytes of one omega digit tile
+    const int STAGE = S * (A_SLICE + tc_nt_max(S) * TC_BK);      // fixed stage pitch
+    const uint32_t stage_tx = (uint32_t)(S * (A_SLICE + B_SLICE));
+    __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = (smem_u32(tc_smem) + 1023u) & ~1023u;   // swizzled tiles want 1024-byte alignment
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_STAGES]);
+    const uint32_t tfull = smem_u32(&bars[2 * TC_STAGES]), tempty = smem_u32(&bars[2 * TC_STAGES + 1]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int acc_cols = 512 / S / 16 * 16;                      // column pitch between the S accumulators
+
+    const long long n_items = (long long)it.n_mtiles * it.n_ntiles * it.n_chunks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0 && !it.probe) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int ntile = (int)(item % it.n_ntiles);
+                const int mtile = (int)((item / it.n_ntiles) % it.n_mtiles);
+                const int chunk = (int)(item / ((long long)it.n_ntiles * it.n_mtiles));
+                const int kb0 = chunk * it.blocks_per_chunk;
+                const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full0 + 8 * stage;
+                    mbar_expect_tx(fb, stage_tx);
+                    const uint32_t sa = sbase + stage * STAGE;
+                    const uint32_t sb = sa + S * A_SLICE;
+#pragma unroll
+                    for (int s = 0; s < S; ++s)
+                        tma_load_2d(sa + s * A_SLICE, &mapZ, kb * TC_BK, (int)(s * it.Mpad + (long long)mtile * TC_BM), fb);
+#pragma unroll
+                    for (int s = 0; s < S; ++s)
+                        tma_load_2d(sb + s * B_SLICE, &mapO, kb * TC_BK, s * it.Npad + ntile * it.nt, fb);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, tphase = 0;
+            uint32_t idesc[2][2];
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) idesc[a][b] = tc_idesc(a, b, it.nt);
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int chunk = (int)(item / ((long long)it.n_ntiles * it.n_mtiles));
+                const int kb0 = chunk * it.blocks_per_chunk;
+                const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+                mbar_wait(tempty, tphase ^ 1);           // epilogue has drained the accumulators of the previous item
+                tc_fence_after();
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    if (!it.probe) mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = sbase + stage * STAGE;
+                    const uint32_t sb = sa + S * A_SLICE;
+                    const uint64_t da = tc_smem_desc(sa), db = tc_smem_desc(sb);
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {
+#pragma unroll
+                        for (int a = 0; a < S; ++a) {
+#pragma unroll
+                            for (int b = 0; b + a < S; ++b) {
+                                const uint64_t adesc = da + (uint64_t)((a * A_SLICE + ks * TC_UK) >> 4);
+                                const uint64_t bdesc = db + (uint64_t)((b * B_SLICE + ks * TC_UK) >> 4);
+                                // first product of order g=a+b in this item overwrites its accumulator
+                                const uint32_t acc = (kb > kb0 || ks > 0 || a > 0) ? 1u : 0u;
+                                tc_mma_i8(tmem + (uint32_t)((a + b) * acc_cols), adesc, bdesc, idesc[a > 0][b > 0], acc);
+                            }
+                        }
+                    }
+                    if (!it.probe) tc_commit(empty0 + 8 * stage);   // frees the stage once the MMAs above have read it
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull);                         // accumulators of this item complete
+                tphase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                     // TMEM lane quarter this warp may read
+        uint32_t tphase = 0;
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int ntile = (int)(item % it.n_ntiles);
+            const int mtile = (int)((item / it.n_ntiles) % it.n_mtiles);
+            mbar_wait(tfull, tphase);
+            tphase ^= 1;
+            tc_fence_after();
+            const long long row = (long long)mtile * TC_BM + quarter * 32 + lane;
+            const int n0 = ntile * it.nt;
+            for (int c0 = 0; c0 < it.nt; c0 += 16) {
+                int r[S][16];
+#pragma unroll
+                for (int g = 0; g < S; ++g)
+                    tc_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * acc_cols + c0), r[g]);
+                tc_ld_wait();
+                if (row < it.M && !it.probe) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        long long v = 0;
+#pragma unroll
+                        for (int g = 0; g < S; ++g) v += (long long)r[g][c] * (1LL << (8 * (S - 1 - g)));
+                        const int n = n0 + c0 + c;
+                        if (n < it.n_valid && v != 0)
+                            atomicAdd(reinterpret_cast<unsigned long long*>(Jint + (long long)n * it.ldj + row),
+                                      (unsigned long long)v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ operand preparation
+// column maxima of a (T x ld) row-major matrix of non-negative entries, as IEEE bit patterns (monotone for x >= 0);
+// *neg is set when a negative entry is seen.  cmax must be zeroed by the caller.
+__global__ void __launch_bounds__(256)
+colmax_kernel(const double* __restrict__ A, int ld, long long T, int ncols, long long rows_per_cta,
+              unsigned long long* __restrict__ cmax, int* __restrict__ neg) {
+    const long long t0 = (long long)blockIdx.y * rows_per_cta;
+    const long long t1 = min(T, t0 + rows_per_cta);
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= ncols) return;
+    double m = 0.0;
+    bool ng = false;
+    for (long long t = t0; t < t1; ++t) {
+        const double v = A[t * ld + c];
+        ng |= (v < 0.0);
+        m = fmax(m, v);
+    }
+    if (ng) atomicExch(neg, 1);
+    atomicMax(cmax + c, (unsigned long long)__double_as_longlong(m));
+}
+
+// S radix-256 digits of round(v): digit 0 (most significant) in [0,255], the others signed in [-128,127]
+template <int S>
+__device__ __forceinline__ void tc_digits(double scaled, unsigned (&d)[S]) {
+    long long v = __double2ll_rn(scaled);
+#pragma unroll
+    for (int s = S - 1; s >= 1; --s) {
+        const long long lo = ((v + 128) & 255) - 128;
+        d[s] = (unsigned)(lo & 255);
+        v = (v - lo) >> 8;
+    }
+    d[0] = (unsigned)(v & 255);
+}
+
+// Zs[s][pair(i,j)][t] for i fixed (blockIdx.y), 32 columns j (blockIdx.x), 128 time bins (blockIdx.z, strided).
+template <int S>
+__global__ void __launch_bounds__(256)
+zslice_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const double* __restrict__ cmax,
+              uint8_t* __restrict__ Zs, long long Mpad, long long Tpad) {
+    const int i = blockIdx.y;
+    const int j0 = blockIdx.x * 32;
+    if (j0 > i) return;
+    __shared__ double xs[32][130];
+    __shared__ double xi[128];
+    const int tid = threadIdx.x;
+    const int jl = tid >> 3, tq = tid & 7;
+    const int j = j0 + jl;
+    const int ei = tc_exponent(cmax[i]);
+    const int ej = (j < D) ? tc_exponent(cmax[j]) : 0;
+    const double scale = ldexp(1.0, 8 * S - ei - ej);
+    const long long p = (long long)i * (i + 1) / 2 + j;
+    for (long long tb = (long long)blockIdx.z * 128; tb < Tpad; tb += (long long)gridDim.z * 128) {
+        __syncthreads();
+        for (int x = tid; x < 128 * 32; x += 256) {
+            const int r = x >> 5, c = x & 31;
+            const long long t = tb + r;
+            xs[c][r] = (t < T && j0 + c <= i) ? Xp[t * ldx + j0 + c] : 0.0;
+        }
+        if (tid < 128) xi[tid] = (tb + tid < T) ? Xp[(tb + tid) * ldx + i] : 0.0;
+        __syncthreads();
+        if (j <= i) {
+            unsigned pk[S][4];
+#pragma unroll
+            for (int s = 0; s < S; ++s) pk[s][0] = pk[s][1] = pk[s][2] = pk[s][3] = 0u;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                unsigned d[S];
+                tc_digits<S>(xs[jl][tq * 16 + k] * xi[tq * 16 + k] * scale, d);
+#pragma unroll
+                for (int s = 0; s < S; ++s) pk[s][k >> 2] |= d[s] << (8 * (k & 3));
+            }
+            if (tb + tq * 16 < Tpad) {
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    *reinterpret_cast<uint4*>(Zs + ((long long)s * Mpad + p) * Tpad + tb + tq * 16) =
+                        make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+            }
+        }
+    }
+}
+
+// Os[s][n][t]: digits of omega[t, n] * 2^(8S - eo_n); tile = 128 time bins x 32 neurons, transposed through smem.
+template <int S>
+__global__ void __launch_bounds__(256)
+oslice_kernel(const double* __restrict__ Om, int ldo, long long T, int n_valid, const double* __restrict__ omax,
+              uint8_t* __restrict__ Os, int Npad, long long Tpad) {
+    __shared__ double ws[32][130];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * 32;
+    const long long tb = (long long)blockIdx.y * 128;
+    for (int x = tid; x < 128 * 32; x += 256) {
+        const int r = x >> 5, c = x & 31;
+        const long long t = tb + r;
+        ws[c][r] = (t < T && n0 + c < n_valid) ? Om[t * ldo + n0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int nl = tid >> 3, tq = tid & 7;
+    const int n = n0 + nl;
+    if (n >= n_valid || tb + tq * 16 >= Tpad) return;
+    const double scale = ldexp(1.0, 8 * S - tc_exponent(omax[n]));
+    unsigned pk[S][4];
+#pragma unroll
+    for (int s = 0; s < S; ++s) pk[s][0] = pk[s][1] = pk[s][2] = pk[s][3] = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        unsigned d[S];
+        tc_digits<S>(ws[nl][tq * 16 + k] * scale, d);
+#pragma unroll
+        for (int s = 0; s < S; ++s) pk[s][k >> 2] |= d[s] << (8 * (k & 3));
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+        *reinterpret_cast<uint4*>(Os + ((long long)s * Npad + n) * Tpad + tb + tq * 16) =
+            make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+}
+
+// J[n][i][j] (i >= j) = Jint[n][pair(i,j)] * 2^(ex_i + ex_j + eo_n - 8 S - 8): the operands carry 2^(8S) each and the
+// order-g accumulators were weighted 256^(S-1-g) instead of 256^(2S-2-g).
+__global__ void __launch_bounds__(256)
+gram_tc_finalize_kernel(const long long* __restrict__ Jint, long long ldjint, const double* __restrict__ cmax,
+                        const double* __restrict__ omax, int D, int S, double* __restrict__ J, long long stride_n, int ldj) {
+    const int n = blockIdx.z;
+    const int i = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j > i) return;
+    const long long p = (long long)i * (i + 1) / 2 + j;
+    const int e = tc_exponent(cmax[i]) + tc_exponent(cmax[j]) + tc_exponent(omax[n]) - 8 * S - 8;
+    J[(long long)n * stride_n + (long long)i * ldj + j] = ldexp((double)Jint[(long long)n * ldjint + p], e);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int tc_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        PYGLM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) {
+            pyglm_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+            return PYGLM_ERR_UNSUPPORTED;
+        }
+        fn = (EncodeTiledFn)p;
+    }
+    *out = fn;
+    return PYGLM_OK;
+}
+
+// digit planes as one 2-D byte tensor: inner dim = time (Tpad), outer dim = S * rows; box = TC_BK bytes x box_rows
+int tc_make_map(CUtensorMap* map, const void* base, long long Tpad, long long rows, int box_rows) {
+    EncodeTiledFn enc;
+    int rc = tc_encode_fn(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)Tpad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Tpad};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = (TC_BK == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (TC_BK == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pyglm_set_error("cuTensorMapEncodeTiled failed (CUresult %d) for Tpad=%lld rows=%lld box_rows=%d", (int)r, Tpad, rows, box_rows);
+        return PYGLM_ERR_CUDA;
+    }
+    return PYGLM_OK;
+}
+
+template <int S>
+int tc_launch(const uint8_t* Zs, const uint8_t* Os, long long* Jint, const TcItems& it, long long Tpad, int max_ctas,
+              cudaStream_t stream) {
+    CUtensorMap mz, mo;
+    int rc = tc_make_map(&mz, Zs, Tpad, (long long)S * it.Mpad, TC_BM);
+    if (rc) return rc;
+    rc = tc_make_map(&mo, Os, Tpad, (long long)S * it.Npad, it.nt);
+    if (rc) return rc;
+    const int smem = TC_STAGES * S * (TC_BM * TC_BK + tc_nt_max(S) * TC_BK) + 1024;
+    PYGLM_CUDA(cudaFuncSetAttribute(gram_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int dev = 0, sms = 0;
+    PYGLM_CUDA(cudaGetDevice(&dev));
+    PYGLM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long items = (long long)it.n_mtiles * it.n_ntiles * it.n_chunks;
+    int grid = (int)((items < sms) ? items : sms);
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    gram_tc_kernel<S><<<grid, TC_THREADS, smem, stream>>>(mz, mo, Jint, it);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
+}  // namespace
+
+// Geometry of the tensor-core Gram for (D, n_valid, T, S): out[0]=M pairs, [1]=Mpad, [2]=Tpad, [3]=Npad, [4]=nt,
+// [5]=n_ntiles, [6]=n_chunks, [7]=blocks_per_chunk.  Returns 0, or an error when S is unsupported.
+extern "C" int pyglm_gram_tc_geometry(int D, int n_valid, long long T, int S, long long* out) {
+    PYGLM_CHECK_ARG(S == 3 || S == 4 || S == 5, "pyglm_gram_tc: S=%d digits unsupported (3, 4 or 5)", S);
+    PYGLM_CHECK_ARG(D > 0 && n_valid > 0 && T > 0 && out, "pyglm_gram_tc_geometry: bad arguments");
+    const long long M = (long long)D * (D + 1) / 2;
+    const long long Mpad = (M + TC_BM - 1) / TC_BM * TC_BM;
+    const long long Tpad = (T + TC_BK - 1) / TC_BK * TC_BK;
+    const int ntmax = tc_nt_max(S);
+    const int n_ntiles = (n_valid + ntmax - 1) / ntmax;
+    const int nt = ((n_valid + n_ntiles - 1) / n_ntiles + 15) / 16 * 16;
+    const long long n_blocks = Tpad / TC_BK;
+    const int max_blocks = TC_KCHUNK / TC_BK;
+    int n_chunks = (int)((n_blocks + max_blocks - 1) / max_blocks);
+    const int bpc = (int)((n_blocks + n_chunks - 1) / n_chunks);
+    n_chunks = (int)((n_blocks + bpc - 1) / bpc);               // no empty chunk
+    out[0] = M; out[1] = Mpad; out[2] = Tpad; out[3] = (long long)n_ntiles * nt; out[4] = nt;
+    out[5] = n_ntiles; out[6] = n_chunks; out[7] = bpc;
+    return PYGLM_OK;
+}
+
+// Column maxima (as doubles) of the first ncols columns of a non-negative (T x ld) matrix; *neg_flag != 0 when a
+// negative entry exists (the tensor-core path then does not apply).  cmax (ncols doubles) and neg_flag (1 int) are
+// overwritten.
+extern "C" int pyglm_column_max(const double* A, int ld, long long T, int ncols, double* cmax, int* neg_flag,
+                                cudaStream_t stream) {
+    PYGLM_CHECK_ARG(A && cmax && neg_flag && T > 0 && ncols > 0 && ncols <= ld, "pyglm_column_max: bad arguments");
+    PYGLM_CUDA(cudaMemsetAsync(cmax, 0, sizeof(double) * ncols, stream));
+    PYGLM_CUDA(cudaMemsetAsync(neg_flag, 0, sizeof(int), stream));
+    long long rows = 256;
+    long long gy = (T + rows - 1) / rows;
+    if (gy > 65535) { rows = (T + 65534) / 65535; gy = (T + rows - 1) / rows; }
+    dim3 grid((ncols + 255) / 256, (unsigned)gy);
+    colmax_kernel<<<grid, 256, 0, stream>>>(A, ld, T, ncols, rows, reinterpret_cast<unsigned long long*>(cmax), neg_flag);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
+// Digits of Z = X~_i X~_j for every pair i >= j (sweep-invariant; once per dataset).
+//   Xp (T x ldx) padded design, cmax (D doubles) from pyglm_column_max, Zs: S * Mpad * Tpad bytes, ZEROED by the caller.
+extern "C" int pyglm_gram_tc_build_z(const double* Xp, int ldx, long long T, int D, const double* cmax, int S,
+                                     unsigned char* Zs, long long Mpad, long long Tpad, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(Xp && cmax && Zs, "pyglm_gram_tc_build_z: null pointer");
+    PYGLM_CHECK_ARG(D <= 65535 && Tpad % TC_BK == 0 && Tpad >= T && Mpad >= (long long)D * (D + 1) / 2,
+                    "pyglm_gram_tc_build_z: bad geometry");
+    long long tb = (Tpad + 127) / 128;
+    dim3 grid((D + 31) / 32, D, (unsigned)(tb > 4096 ? 4096 : tb));
+    switch (S) {
+        case 3: zslice_kernel<3><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad); break;
+        case 4: zslice_kernel<4><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad); break;
+        case 5: zslice_kernel<5><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad); break;
+        default: pyglm_set_error("pyglm_gram_tc_build_z: S=%d unsupported", S); return PYGLM_ERR_INVALID;
+    }
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
+// Per sweep: digits of omega (T x ldo, n_valid columns) -> Os (S * Npad * Tpad bytes, rows >= n_valid stay zero:
+// ZEROED once by the caller); omax (n_valid doubles) and neg_flag are overwritten.
+extern "C" int pyglm_gram_tc_slice_omega(const double* Om, int ldo, long long T, int n_valid, int S, double* omax,
+                                         int* neg_flag, unsigned char* Os, int Npad, long long Tpad, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(Om && omax && Os && neg_flag, "pyglm_gram_tc_slice_omega: null pointer");
+    PYGLM_CHECK_ARG(Tpad % TC_BK == 0 && Tpad >= T && Npad >= n_valid, "pyglm_gram_tc_slice_omega: bad geometry");
+    int rc = pyglm_column_max(Om, ldo, T, n_valid, omax, neg_flag, stream);
+    if (rc) return rc;
+    long long gy = (Tpad + 127) / 128;
+    PYGLM_CHECK_ARG(gy <= 65535, "pyglm_gram_tc_slice_omega: T too large for one launch");
+    dim3 grid((n_valid + 31) / 32, (unsigned)gy);
+    switch (S) {
+        case 3: oslice_kernel<3><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad); break;
+        case 4: oslice_kernel<4><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad); break;
+        case 5: oslice_kernel<5><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad); break;
+        default: pyglm_set_error("pyglm_gram_tc_slice_omega: S=%d unsupported", S); return PYGLM_ERR_INVALID;
+    }
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
+// The tcgen05 integer GEMM: Jint[n][pair] = sum_t sum_{a+b<S} 256^(S-1-a-b) zs[a][pair][t] os[b][n][t]  (exact).
+// Jint: n_valid rows of pitch ldjint >= Mpad int64, overwritten.  max_ctas <= 0: one CTA per SM.
+static int gram_tc_mma_impl(const unsigned char* Zs, const unsigned char* Os, int D, int n_valid, long long T, int S,
+                            long long* Jint, long long ldjint, int max_ctas, int probe, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(Zs && Os && Jint, "pyglm_gram_tc_mma: null pointer");
+    long long g[8];
+    int rc = pyglm_gram_tc_geometry(D, n_valid, T, S, g);
+    if (rc) return rc;
+    PYGLM_CHECK_ARG(ldjint >= g[1], "pyglm_gram_tc_mma: ldjint=%lld < Mpad=%lld", ldjint, g[1]);
+    PYGLM_CHECK_ARG(((uintptr_t)Zs & 127) == 0 && ((uintptr_t)Os & 127) == 0, "pyglm_gram_tc_mma: digit planes must be 128-byte aligned");
+    PYGLM_CHECK_ARG((long long)S * g[1] < (1LL << 31) && g[2] < (1LL << 31), "pyglm_gram_tc_mma: problem too large for 32-bit TMA coordinates");
+    TcItems it;
+    it.M = g[0]; it.Mpad = g[1]; it.Npad = (int)g[3]; it.nt = (int)g[4]; it.n_ntiles = (int)g[5];
+    it.n_chunks = (int)g[6]; it.blocks_per_chunk = (int)g[7]; it.n_blocks = (int)(g[2] / TC_BK);
+    it.n_mtiles = (int)(g[1] / TC_BM); it.n_valid = n_valid; it.ldj = ldjint; it.probe = probe;
+    PYGLM_CUDA(cudaMemsetAsync(Jint, 0, sizeof(long long) * (size_t)n_valid * (size_t)ldjint, stream));
+    switch (S) {
+        case 3: return tc_launch<3>(Zs, Os, Jint, it, g[2], max_ctas, stream);
+        case 4: return tc_launch<4>(Zs, Os, Jint, it, g[2], max_ctas, stream);
+        case 5: return tc_launch<5>(Zs, Os, Jint, it, g[2], max_ctas, stream);
+    }
+    return PYGLM_ERR_INVALID;
+}
+
+extern "C" int pyglm_gram_tc_mma(const unsigned char* Zs, const unsigned char* Os, int D, int n_valid, long long T, int S,
+                                 long long* Jint, long long ldjint, int max_ctas, cudaStream_t stream) {
+    return gram_tc_mma_impl(Zs, Os, D, n_valid, T, S, Jint, ldjint, max_ctas, 0, stream);
+}
+
+// Measurement hook: the MMA schedule of pyglm_gram_tc_mma with operand loads and result atomics removed (the tensor
+// cores multiply whatever shared memory holds).  Its duration gives the achievable int8 tcgen05 rate of this tile
+// shape, the denominator profiles/ quotes beside the 2 x bf16 figure.  Jint is zeroed and otherwise untouched.
+extern "C" int pyglm_gram_tc_mma_probe(const unsigned char* Zs, const unsigned char* Os, int D, int n_valid, long long T,
+                                       int S, long long* Jint, long long ldjint, cudaStream_t stream) {
+    return gram_tc_mma_impl(Zs, Os, D, n_valid, T, S, Jint, ldjint, 0, 1, stream);
+}
+
+// J[n][i][j] (lower triangle, pitch ldj, stride_n between neurons) from the exact integer sums and the scales.
+extern "C" int pyglm_gram_tc_finalize(const long long* Jint, long long ldjint, const double* cmax, const double* omax,
+                                      int D, int n_valid, int S, double* J, long long stride_n, int ldj, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(Jint && cmax && omax && J, "pyglm_gram_tc_finalize: null pointer");
+    PYGLM_CHECK_ARG(D <= 65535 && n_valid <= 65535 && ldj >= D, "pyglm_gram_tc_finalize: bad geometry");
+    dim3 grid((D + 255) / 256, D, n_valid);
+    gram_tc_finalize_kernel<<<grid, 256, 0, stream>>>(Jint, ldjint, cmax, omax, D, S, J, stride_n, ldj);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from .distributed import Comm, block_partition
-from .kernels import CudaKernels, pad_ldn, pad_ldx
+from .kernels import CudaKernels, gram_tc_bytes, pad_ldn, pad_ldx
 from .priors import prior_arrays
 
 _KERNELS = {}
@@ -50,8 +50,13 @@ class DeviceDataset(object):
 
 
 class GibbsEngine(object):
-    def __init__(self, N, B, kernels=None, seed=0, comm=None, shard="neuron"):
+    def __init__(self, N, B, kernels=None, seed=0, comm=None, shard="neuron", gram="auto", gram_digits=4):
+        """gram: "fp64" = FP64 DMMA kernel (gram.cu); "tc" = tcgen05 integer-digit kernel (gram_tc.cu), error
+        <= 1e-9 relative against FP64; "auto" = "tc" when the design is non-negative, the contraction is large
+        enough to matter and the digit planes of Z fit in HBM, else "fp64"."""
         assert shard in ("neuron", "time")
+        assert gram in ("auto", "fp64", "tc") and gram_digits in (3, 4, 5)
+        self.gram_mode, self.gram_digits = gram, gram_digits
         self.N, self.B = N, B
         self.D = N * B + 1
         self.ldx = pad_ldx(self.D)
@@ -73,6 +78,22 @@ class GibbsEngine(object):
         # draws of the next sweeps with the given host arrays (row n = postsynaptic neuron n), so that a whole
         # sweep can be compared with the reference on identical randomness.  None in production.
         self.inject = None
+        # Optional per-phase device timing: set to {} and every sweep appends (start, end) CUDA-event pairs per
+        # phase name; phase_ms() averages them.  Events are recorded on the launching stream.
+        self.profile = None
+
+    def _mark(self, name, start=None):
+        if self.profile is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if start is not None:
+            self.profile.setdefault(name, []).append((start, ev))
+        return ev
+
+    def phase_ms(self):
+        torch.cuda.synchronize()
+        return {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in (self.profile or {}).items()}
 
     # ------------------------------------------------------------------ data
     def make_dataset(self, Y, basis=None, X=None, t_off=0, T_global=None):
@@ -102,6 +123,45 @@ class GibbsEngine(object):
         if key not in self._ws:
             self._ws[key] = (self.K.zeros if zero else self.K.empty)(*shape, dtype=dtype)
         return self._ws[key]
+
+    # ------------------------------------------------------------------ Gram dispatch
+    TC_MIN_WORK = 2e11          # pairs * T * neurons below which the FP64 kernel is already sub-millisecond
+
+    def _tc_plan(self, ds, n):
+        """The dataset's tensor-core Gram plan for n local neurons, or None when the FP64 kernel should run."""
+        if self.gram_mode == "fp64":
+            return None
+        key = ("tc_plan", n, self.gram_digits)
+        if key not in ds.buffers:
+            plan = None
+            M = self.D * (self.D + 1) // 2
+            need = gram_tc_bytes(self.D, n, ds.T, self.gram_digits)
+            want = self.gram_mode == "tc" or float(M) * ds.T * n >= self.TC_MIN_WORK
+            free = torch.cuda.mem_get_info(self.K.device)[0] if want else 0
+            if want and need < 0.9 * free:
+                try:
+                    plan = self.K.gram_tc_plan(ds.Xp, self.D, n, self.gram_digits)
+                except ValueError:
+                    plan = None          # signed design: digits of Z assume x >= 0
+            if plan is None and self.gram_mode == "tc":
+                raise RuntimeError("gram='tc' needs a non-negative design and %.1f GB of free HBM (%.1f GB free)"
+                                   % (need / 1e9, free / 1e9))
+            ds.buffers[key] = plan
+        return ds.buffers[key]
+
+    def weighted_gram(self, ds, omega, n, J):
+        plan = self._tc_plan(ds, n)
+        if plan is not None:
+            e0 = self._mark("gram_tc_slice")
+            plan.slice_omega(omega)
+            e1 = self._mark("gram_tc_slice", e0)
+            plan.mma()
+            e2 = self._mark("gram_tc_mma", e1)
+            plan.finalize(J)
+            self._mark("gram_tc_finalize", e2)
+        else:
+            self.K.weighted_gram(ds.Xp, omega, self.D, n, J=J)
+        return J
 
     # ------------------------------------------------------------------ coefficients
     def build_Wt(self, A, W, b, lo, hi):
@@ -148,18 +208,22 @@ class GibbsEngine(object):
             for di, ds in enumerate(datasets):
                 psi = self._buf(ds, "psi", (ds.T, ldn))
                 omega = self._buf(ds, "omega", (ds.T, ldn), zero=True)
+                e0 = self._mark("activation")
                 K.activation(ds.Xp, Wt, D, nP, out=psi)
+                e1 = self._mark("activation", e0)
                 if self.inject is None:
                     K.pg_draw(psi, nP, omega, self.seed, call_base + di, ds.t_off, p_lo, N)
                 else:
                     om = np.asarray(self.inject["omega"][di])[ds.t_off:ds.t_off + ds.T, p_lo:p_hi]
                     omega[:, :nP] = K.to_device(om)
+                e2 = self._mark("pg_draw", e1)
                 if di == 0:
-                    K.weighted_gram(ds.Xp, omega, D, nP, J=J)
+                    self.weighted_gram(ds, omega, nP, J)
                 else:
                     Jd = self._wsbuf("J_extra", (nP, ldx, ldx), zero=True)
-                    K.weighted_gram(ds.Xp, omega, D, nP, J=Jd)
+                    self.weighted_gram(ds, omega, nP, Jd)
                     J += Jd
+                self._mark("weighted_gram", e2)
             if self.shard == "time" and comm.world > 1:
                 # partial Grams of ALL neurons over the local time slab -> complete Grams of the local block
                 Jpad = J
@@ -188,8 +252,10 @@ class GibbsEngine(object):
                 us = K.to_device(np.asarray(self.inject["us"][s_lo:s_hi], dtype=np.float64))
                 z = K.to_device(np.asarray(self.inject["z"][s_lo:s_hi], dtype=np.float64))
             P_ws = self._wsbuf("P", (nS * D * D,))
+            e3 = self._mark("spike_slab")
             W_new, b_new, _, _, status = K.spike_slab_update(N, B, J_S, h_S, prior, perm, us, z,
                                                              K.to_device(do_scan.astype(np.uint8)), a_dev, P_ws=P_ws)
+            self._mark("spike_slab", e3)
         else:
             a_dev = K.zeros(0, N, dtype=torch.uint8)
             W_new, b_new = K.zeros(0, N, B), K.zeros(0)

@@ -164,6 +164,26 @@ class CudaKernels(object):
                    self._stream(), launches=2 if nslabs > 1 else 1)
         return rows[:, D - 1 - i_base, :].contiguous()
 
+    # ------------------------------------------------------------------ (3') weighted Gram on tcgen05
+    def gram_tc_geometry(self, D, n_valid, T, S):
+        g = (ctypes.c_longlong * 8)()
+        cabi.call("pyglm_gram_tc_geometry", D, n_valid, T, S, ctypes.cast(g, ctypes.c_void_p))
+        keys = ("M", "Mpad", "Tpad", "Npad", "nt", "n_ntiles", "n_chunks", "blocks_per_chunk")
+        return dict(zip(keys, [int(v) for v in g]))
+
+    def column_max(self, A, ncols):
+        """(cmax (ncols,) f64, has_negative bool) of the first ncols columns of a (T, ld) device matrix."""
+        T, ld = A.shape
+        cmax = self.empty(ncols)
+        neg = self.empty(1, dtype=torch.int32)
+        self._call("pyglm_column_max", self._p(A), ld, T, ncols, self._p(cmax), self._p(neg), self._stream())
+        return cmax, bool(neg.item())
+
+    def gram_tc_plan(self, Xp, D, n_valid, S=4):
+        """Build the sweep-invariant digit planes of Z = X~_i X~_j (once per dataset) and allocate the per-sweep
+        buffers of the tensor-core Gram.  Raises ValueError when the design has negative entries."""
+        return TcGramPlan(self, Xp, D, n_valid, S)
+
     # ------------------------------------------------------------------ (4) spike and slab
     def scan_randomness(self, N, B, n_loc, n_off, seed, call_id):
         D = N * B + 1
@@ -194,3 +214,62 @@ class CudaKernels(object):
                    self._p(us), self._p(z), z.shape[1], self._p(do_scan), self._p(a), self._p(W), self._p(bias),
                    self._p(P_ws), self._p(logodds), self._p(ml), self._p(status), self._stream())
         return W, bias, logodds, ml, status
+
+
+def gram_tc_bytes(D, n_valid, T, S=4):
+    """HBM bytes the tensor-core Gram keeps resident for one dataset (digit planes of Z and omega, Jint)."""
+    M = D * (D + 1) // 2
+    Mpad, Tpad = round_up(M, 128), round_up(T, 64)
+    return S * Mpad * Tpad + S * round_up(n_valid, 16) * Tpad * 2 + n_valid * Mpad * 8
+
+
+class TcGramPlan(object):
+    """Resident state of the tcgen05 Gram for one dataset: Zs (S, Mpad, Tpad) uint8 digit planes of the
+    Khatri-Rao operand (built once), Os (S, Npad, Tpad) digit planes of omega and Jint (n, Mpad) int64 (per sweep)."""
+
+    def __init__(self, K, Xp, D, n_valid, S=4):
+        self.K, self.D, self.n, self.S = K, D, n_valid, S
+        self.T, self.ldx = Xp.shape
+        g = K.gram_tc_geometry(D, n_valid, self.T, S)
+        self.geom = g
+        self.cmax, neg = K.column_max(Xp, D)
+        if neg:
+            raise ValueError("tensor-core Gram needs a non-negative design matrix")
+        self.Zs = torch.zeros(S, g["Mpad"], g["Tpad"], dtype=torch.uint8, device=K.device)
+        K._call("pyglm_gram_tc_build_z", K._p(Xp), self.ldx, self.T, D, K._p(self.cmax), S, K._p(self.Zs),
+                g["Mpad"], g["Tpad"], K._stream())
+        self.Os = torch.zeros(S, g["Npad"], g["Tpad"], dtype=torch.uint8, device=K.device)
+        self.omax = K.empty(n_valid)
+        self.neg = K.empty(1, dtype=torch.int32)
+        self.Jint = K.empty(n_valid, g["Mpad"], dtype=torch.int64)
+
+    def slice_omega(self, Om):
+        K, g = self.K, self.geom
+        K._call("pyglm_gram_tc_slice_omega", K._p(Om), Om.shape[1], self.T, self.n, self.S, K._p(self.omax),
+                K._p(self.neg), K._p(self.Os), g["Npad"], g["Tpad"], K._stream(), launches=2)
+
+    def mma(self, max_ctas=0):
+        K, g = self.K, self.geom
+        K._call("pyglm_gram_tc_mma", K._p(self.Zs), K._p(self.Os), self.D, self.n, self.T, self.S, K._p(self.Jint),
+                g["Mpad"], max_ctas, K._stream())
+        return self.Jint
+
+    def mma_probe(self):
+        """Issue-rate probe of the MMA schedule (no loads, no atomics): measures the int8 tensor-pipe peak."""
+        K, g = self.K, self.geom
+        K._call("pyglm_gram_tc_mma_probe", K._p(self.Zs), K._p(self.Os), self.D, self.n, self.T, self.S,
+                K._p(self.Jint), g["Mpad"], K._stream())
+
+    def finalize(self, J):
+        K, g = self.K, self.geom
+        K._call("pyglm_gram_tc_finalize", K._p(self.Jint), g["Mpad"], K._p(self.cmax), K._p(self.omax), self.D,
+                self.n, self.S, K._p(J), J.shape[1] * J.shape[2], J.shape[2], K._stream())
+        return J
+
+    def gram(self, Om, J=None):
+        """J[n, i, j] (i >= j) = sum_t Xp[t,i] Xp[t,j] Om[t,n] for Om > 0."""
+        if J is None:
+            J = self.K.zeros(self.n, self.ldx, self.ldx)
+        self.slice_omega(Om)
+        self.mma()
+        return self.finalize(J)

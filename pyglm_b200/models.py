@@ -6,7 +6,7 @@
 The public attributes and call signatures are the reference's (models.py:28-236); what changes is where the
 work happens: add_data filters on the GPU, resample_model runs one GibbsEngine.sweep for all N regressions at
 once (the reference loops over them, models.py:169-171), and log_likelihood / means are single fused kernels.
-Extra keyword-only arguments (`seed`, `shard`, `device`) default to reference behaviour.
+Extra keyword-only arguments (`seed`, `shard`, `gram`) default to reference behaviour.
 """
 import numpy as np
 
@@ -37,7 +37,7 @@ class NonlinearAutoregressiveModel(object):
     """The neuroscience "GLM": a nonlinear vector autoregression, one regression per observed dimension
     (models.py:8-201)."""
 
-    def __init__(self, N, regressions, basis=None, B=10, seed=None, shard="neuron", comm=None):
+    def __init__(self, N, regressions, basis=None, B=10, seed=None, shard="neuron", comm=None, gram="auto"):
         self.N = N
         assert len(regressions) == N
         self.regressions = regressions
@@ -52,6 +52,7 @@ class NonlinearAutoregressiveModel(object):
         self._seed = int(np.random.randint(2 ** 31 - 1)) if seed is None else int(seed)
         self._shard = shard
         self._comm = comm
+        self._gram = gram
         self._engine = None
         self._dev = {}           # (id(X), id(Y)) -> (X, Y, DeviceDataset): keeps the keys alive
 
@@ -73,7 +74,8 @@ class NonlinearAutoregressiveModel(object):
     def engine(self):
         if self._engine is None:
             from .engine import GibbsEngine
-            self._engine = GibbsEngine(self.N, self.B, seed=self._seed, comm=self._comm, shard=self._shard)
+            self._engine = GibbsEngine(self.N, self.B, seed=self._seed, comm=self._comm, shard=self._shard,
+                                       gram=self._gram)
         return self._engine
 
     def _time_slab(self, T):

@@ -207,6 +207,66 @@ def test_weighted_gram_matches_oracle(K, T, N, B, n_loc, nslabs):
         np.testing.assert_allclose(h[j, :D], hr, rtol=RTOL, atol=1e-11)
 
 
+# ----------------------------------------------------------------------------- (3') weighted Gram on tcgen05
+def _tc_inputs(K, T, N, B, n_loc, seed):
+    from pyglm_b200.kernels import pad_ldn
+    rng = np.random.default_rng(seed)
+    Y = spikes(T, N, seed=seed)
+    L = 20
+    basis = O.cosine_basis(B, L) / L
+    Xp = design(K, Y, basis)
+    X = O.convolve_with_basis(Y, basis).reshape(T, N * B)
+    om = np.zeros((T, pad_ldn(n_loc)))
+    om[:, :n_loc] = 0.01 + rng.random((T, n_loc)) ** 3          # skewed like PG draws, max ~1
+    return Xp, X, om
+
+
+@pytest.mark.parametrize("T,N,B,n_loc,S", [(1000, 5, 2, 7, 4), (333, 3, 1, 3, 3), (700, 8, 2, 20, 5),
+                                           (130, 4, 3, 33, 4)])
+def test_gram_tc_integer_sums_are_exact(K, T, N, B, n_loc, S):
+    """Digit planes and the tcgen05 int32/int64 sums against the numpy emulation: bit-exact (integer work)."""
+    Xp, X, om = _tc_inputs(K, T, N, B, n_loc, seed=T)
+    D = N * B + 1
+    plan = K.gram_tc_plan(Xp, D, n_loc, S)
+    Xt = Xp.cpu().numpy()[:, :D]
+    g = plan.geom
+    Jint_ref, J_ref = O.tc_gram_reference(Xt, om[:, :n_loc], S)
+    plan.slice_omega(K.to_device(om))
+    Zs = plan.Zs.cpu().numpy()
+    ex = [O.tc_exponent(c) for c in Xt.max(0)]
+    for (i, j) in [(0, 0), (D - 1, 0), (D - 1, D - 1), (D // 2, D // 3)]:
+        zd = O.tc_digits(Xt[:, j] * Xt[:, i] * 2.0 ** (8 * S - ex[i] - ex[j]), S)
+        for s in range(S):
+            np.testing.assert_array_equal(Zs[s, i * (i + 1) // 2 + j, :T], (zd[s] & 255).astype(np.uint8))
+    assert Zs[:, :, T:].max(initial=0) == 0 and Zs[:, g["M"]:].max(initial=0) == 0
+    Jint = plan.mma().cpu().numpy()
+    np.testing.assert_array_equal(Jint[:, :g["M"]], Jint_ref)
+    J = plan.finalize(K.zeros(n_loc, plan.ldx, plan.ldx)).cpu().numpy()
+    np.testing.assert_array_equal(np.tril(J[:, :D, :D]), J_ref)
+
+
+@pytest.mark.parametrize("T,N,B,n_loc,S", [(40000, 16, 2, 40, 4), (20000, 10, 2, 200, 4), (5000, 27, 3, 27, 5),
+                                           (60000, 6, 2, 12, 4)])
+def test_gram_tc_matches_oracle(K, T, N, B, n_loc, S):
+    """J from the tensor-core kernel against the oracle's FP64 X^T diag(omega) X (regression.py:251-256): <= 1e-9."""
+    Xp, X, om = _tc_inputs(K, T, N, B, n_loc, seed=T + 1)
+    D = N * B + 1
+    plan = K.gram_tc_plan(Xp, D, n_loc, S)
+    J = plan.gram(K.to_device(om)).cpu().numpy()
+    J2 = plan.gram(K.to_device(om)).cpu().numpy()
+    np.testing.assert_array_equal(J, J2)                        # integer atomics: bitwise reproducible
+    for j in list(range(min(n_loc, 3))) + [n_loc - 1]:
+        Jr, _ = O.lkhd_sufficient_statistics(X, om[:, j], np.zeros(T))
+        np.testing.assert_allclose(np.tril(J[j, :D, :D]), np.tril(Jr), rtol=RTOL, atol=0)
+
+
+def test_gram_tc_rejects_signed_design(K):
+    rng = np.random.default_rng(3)
+    Xp = K.pack_design(K.to_device(rng.standard_normal((200, 8))))
+    with pytest.raises(ValueError):
+        K.gram_tc_plan(Xp, 9, 4, 4)
+
+
 # ----------------------------------------------------------------------------- (4) spike and slab
 def prior_tensors(K, hyper_list, N, B):
     """list (one per local neuron) of dict(rho, mu_w, S_w, mu_b, S_b) -> device prior dict"""

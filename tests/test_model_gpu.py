@@ -65,14 +65,16 @@ def test_golden_model_values(golden):
     assert model.log_likelihood([g["tm_Y"].astype(float)]) == pytest.approx(float(g["tm_ll"]), rel=1e-11)
 
 
-def test_full_sweep_matches_reference_on_injected_randomness(golden):
+@pytest.mark.parametrize("gram", ["fp64", "tc"])
+def test_full_sweep_matches_reference_on_injected_randomness(golden, gram):
     """One resample_regressions() of the reference itself (fixture full_sweep.npz) reproduced through the
-    public API with the same omega / permutation / uniforms / normals."""
+    public API with the same omega / permutation / uniforms / normals -- with the FP64 DMMA Gram and with the
+    tcgen05 integer-digit Gram."""
     from pyglm_b200.models import SparseBernoulliGLM
     g = golden("full_sweep.npz")
     N, B = int(g["N"]), int(g["B"])
     np.random.seed(0)
-    m = SparseBernoulliGLM(N, basis=g["basis"], regression_kwargs=dict(S_w=10.0, mu_b=-2., rho=0.3))
+    m = SparseBernoulliGLM(N, basis=g["basis"], regression_kwargs=dict(S_w=10.0, mu_b=-2., rho=0.3), gram=gram)
     for n in range(N):
         m.regressions[n].a, m.regressions[n].W, m.regressions[n].b = g["A0"][n], g["W0"][n], g["b0"][n:n + 1]
     m.add_data(g["Y"].astype(float))
