@@ -26,11 +26,10 @@
 // own draws; in production those buffers are filled by pyglm_scan_randomness (Philox, below).
 #include "common.cuh"
 #include "philox.cuh"
+#include <stdlib.h>
 
 namespace {
 
-constexpr int SS_THREADS = 512;
-constexpr int SS_WARPS = SS_THREADS / 32;
 constexpr int SS_BMAX = 16;
 
 struct SpikeSlabArgs {
@@ -56,7 +55,10 @@ struct SpikeSlabArgs {
     int* status;                                       // (n_loc,) 0 ok, 1 = a Schur complement lost positive definiteness
 };
 
+template <int SS_THREADS>
 struct Ctx {
+    static constexpr int SS_WARPS = SS_THREADS / 32;
+    static constexpr int SS_ROWS = 4;          // rows of P per warp per batch in the passes over P
     // problem
     int N, B, D, NB, ldj, ldp;
     const double* Jn; const double* hn; const double* J0w; const double* h0w; double J0b, h0b;
@@ -135,32 +137,47 @@ struct Ctx {
             cb[c1 * B + bb] = Jp(cidx[c1], coord0 + bb);
         }
         __syncthreads();
-        // t = P c, one warp per row, four right-hand sides per pass
-        for (int c1 = warp; c1 < K; c1 += SS_WARPS) {
-            const double* prow = P + (size_t)c1 * ldp;
+        // t = P c: SS_ROWS rows per warp at a time, four right-hand sides per pass.  All 4*SS_ROWS loads of a lane
+        // are issued before the first FMA, so a pass over P costs a handful of L2 latencies instead of one per row
+        // (P lives in L2: K*K doubles do not fit in shared memory).
+        for (int r0 = warp * SS_ROWS; r0 < K; r0 += SS_WARPS * SS_ROWS) {
             for (int b0 = 0; b0 < bs; b0 += 4) {
-                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                for (int c0 = lane; c0 < K; c0 += 128) {
-                    double pv[4];
+                const int nb = min(4, bs - b0);
+                double s[SS_ROWS][4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) pv[u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;   // 4 loads in flight
+                for (int rr = 0; rr < SS_ROWS; ++rr) s[rr][0] = s[rr][1] = s[rr][2] = s[rr][3] = 0.0;
+                for (int c0 = lane; c0 < K; c0 += 128) {
+                    double pv[SS_ROWS][4];
+#pragma unroll
+                    for (int rr = 0; rr < SS_ROWS; ++rr) {
+                        const double* prow = P + (size_t)min(r0 + rr, K - 1) * ldp;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) pv[rr][u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;
+                    }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int c2 = min(c0 + 32 * u, K - 1);
-                        const double p = pv[u];
-                        const double* cr = cb + c2 * B + b0;
-                        s0 += p * cr[0];
-                        if (b0 + 1 < bs) s1 += p * cr[1];
-                        if (b0 + 2 < bs) s2 += p * cr[2];
-                        if (b0 + 3 < bs) s3 += p * cr[3];
+                        const double* cr = cb + min(c0 + 32 * u, K - 1) * B + b0;
+                        const double v0 = cr[0];
+                        const double v1 = (nb > 1) ? cr[1] : 0.0;
+                        const double v2 = (nb > 2) ? cr[2] : 0.0;
+                        const double v3 = (nb > 3) ? cr[3] : 0.0;
+#pragma unroll
+                        for (int rr = 0; rr < SS_ROWS; ++rr) {
+                            s[rr][0] += pv[rr][u] * v0;
+                            s[rr][1] += pv[rr][u] * v1;
+                            if (nb > 2) { s[rr][2] += pv[rr][u] * v2; s[rr][3] += pv[rr][u] * v3; }
+                        }
                     }
                 }
-                s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-                if (lane == 0) {
-                    tb[c1 * B + b0] = s0;
-                    if (b0 + 1 < bs) tb[c1 * B + b0 + 1] = s1;
-                    if (b0 + 2 < bs) tb[c1 * B + b0 + 2] = s2;
-                    if (b0 + 3 < bs) tb[c1 * B + b0 + 3] = s3;
+#pragma unroll
+                for (int rr = 0; rr < SS_ROWS; ++rr) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < nb) {
+                            const double v = warp_sum(s[rr][k]);
+                            if (lane == 0 && r0 + rr < K) tb[(r0 + rr) * B + b0 + k] = v;
+                        }
+                    }
                 }
             }
         }
@@ -205,6 +222,38 @@ struct Ctx {
         __syncthreads();
     }
 
+    // P[c1][c2] += sign * sum_k gb[c1][k] tb[c2][k] over the K x K active block, SS_ROWS rows per warp with every
+    // load of the batch in flight before the first store.
+    __device__ __forceinline__ void rank_update(int bs, double sign) {
+        for (int r0 = warp * SS_ROWS; r0 < K; r0 += SS_WARPS * SS_ROWS) {
+            for (int c0 = lane; c0 < K; c0 += 128) {
+                double pv[SS_ROWS][4];
+#pragma unroll
+                for (int rr = 0; rr < SS_ROWS; ++rr) {
+                    const double* prow = P + (size_t)min(r0 + rr, K - 1) * ldp;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) pv[rr][u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c2 = c0 + 32 * u;
+                    if (c2 < K) {
+                        const double* t2 = tb + c2 * B;
+#pragma unroll
+                        for (int rr = 0; rr < SS_ROWS; ++rr) {
+                            if (r0 + rr < K) {
+                                const double* g1 = gb + (r0 + rr) * B;
+                                double acc = 0.0;
+                                for (int k = 0; k < bs; ++k) acc += g1[k] * t2[k];
+                                P[(size_t)(r0 + rr) * ldp + c2] = pv[rr][u] + sign * acc;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
     // Append the block evaluated by the last eval_add.
     __device__ void commit_add(int coord0, int bs, bool draw) {
         for (int e = tid; e < K * bs; e += SS_THREADS) {          // gb = t G
@@ -214,25 +263,7 @@ struct Ctx {
             gb[c1 * B + bb] = s;
         }
         __syncthreads();
-        for (int c1 = warp; c1 < K; c1 += SS_WARPS) {             // P += gb t^T
-            double* prow = P + (size_t)c1 * ldp;
-            const double* g1 = gb + c1 * B;
-            for (int c0 = lane; c0 < K; c0 += 128) {
-                double pv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) pv[u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c2 = c0 + 32 * u;
-                    if (c2 < K) {
-                        const double* t2 = tb + c2 * B;
-                        double s = 0.0;
-                        for (int k = 0; k < bs; ++k) s += g1[k] * t2[k];
-                        prow[c2] = pv[u] + s;
-                    }
-                }
-            }
-        }
+        rank_update(bs, 1.0);                                      // P += gb t^T
         for (int e = tid; e < K * bs; e += SS_THREADS) {          // new border rows / columns
             const int c1 = e / bs, bb = e - c1 * bs;
             const double v = -gb[c1 * B + bb];
@@ -290,25 +321,7 @@ struct Ctx {
             gb[c1 * B + bb] = s;
         }
         __syncthreads();
-        for (int c1 = warp; c1 < K; c1 += SS_WARPS) {             // P -= gb tb^T
-            double* prow = P + (size_t)c1 * ldp;
-            const double* g1 = gb + c1 * B;
-            for (int c0 = lane; c0 < K; c0 += 128) {
-                double pv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) pv[u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c2 = c0 + 32 * u;
-                    if (c2 < K) {
-                        const double* t2 = tb + c2 * B;
-                        double s = 0.0;
-                        for (int k = 0; k < B; ++k) s += g1[k] * t2[k];
-                        prow[c2] = pv[u] - s;
-                    }
-                }
-            }
-        }
+        rank_update(B, -1.0);                                      // P -= gb tb^T
         for (int c1 = tid; c1 < K; c1 += SS_THREADS) {            // mu_R -= P_Rm P_mm^-1 mu_m   (r holds mu_m)
             double s = 0.0;
             for (int k = 0; k < B; ++k) s += gb[c1 * B + k] * r[k];
@@ -337,14 +350,15 @@ struct Ctx {
     }
 };
 
-__global__ void __launch_bounds__(SS_THREADS)
+template <int SS_THREADS, int MINB>
+__global__ void __launch_bounds__(SS_THREADS, MINB)
 spike_slab_kernel(SpikeSlabArgs A) {
     extern __shared__ __align__(16) double ssm[];
     const int ln = blockIdx.x;
     const int N = A.N, B = A.B, D = A.D;
     const int Dpad = (D + 1) & ~1;
 
-    Ctx c;
+    Ctx<SS_THREADS> c;
     c.N = N; c.B = B; c.D = D; c.NB = N * B; c.ldj = A.ldj; c.ldp = D;
     c.Jn = A.J + (size_t)ln * A.stride_n;
     c.hn = A.h + (size_t)ln * A.ldh;
@@ -449,6 +463,488 @@ spike_slab_kernel(SpikeSlabArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path, B <= 4 (every configuration in BASELINE.json has B in {1,2,3}).  Same algorithm and the same order of
+// updates as the generic kernel above; what changes is how a step is executed:
+//   * B is a template parameter: block loops unroll, index divisions fold, and the three phases (build, scan, draw)
+//     run through ONE loop so each step routine is instantiated once (the generic kernel is 390 KB of SASS and
+//     stalls on instruction fetch);
+//   * the small dense algebra of a step (Cholesky of the B x B Schur complement, log-determinant, quadratic form,
+//     the flip decision, and -- only when the step is committed -- the inverse) is evaluated REDUNDANTLY by every
+//     thread in registers from block-wide partial sums, instead of by thread 0 with 511 threads parked at a barrier;
+//   * S_m = J_mm - c^T P c and r = h_m - c^T mu are accumulated inside the pass over P (each warp multiplies the
+//     rows of t it has just produced), so an evaluation is two barriers, a rejected removal none;
+//   * passes over P keep 16 loads per lane in flight (4 rows x 4 column chunks): P lives in L2 (K x K doubles do
+//     not fit in shared memory), so memory-level parallelism sets the time of a pass;
+//   * t G (the scaled border) is recomputed per row from registers in the rank update: no staging pass.
+template <int B>
+struct SmallSolve {
+    double L[B][B], il[B], y[B];      // Cholesky factor, 1/diag, L^-1 r
+    double G[B][B], gr[B], xm[B];     // (L L^T)^-1, G r, L^-T z
+    double dpost;
+};
+
+// Cholesky of the lower triangle of S (BS x BS) and the quadratic form: dpost = sgn 1/2 log|S| + 1/2 r^T S^-1 r
+// (NaN when S is not positive definite).
+template <int B, int BS>
+__device__ __forceinline__ void small_factor(SmallSolve<B>& w, const double (&S)[B][B], const double (&r)[B], double sgn) {
+    double det = 1.0, q = 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+        double d = S[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= w.L[j][k] * w.L[j][k];
+        ok = ok && (d > 0.0);
+        det *= d;
+        w.il[j] = rsqrt(d);
+        w.L[j][j] = d * w.il[j];
+#pragma unroll
+        for (int i = j + 1; i < BS; ++i) {
+            double v = S[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= w.L[i][k] * w.L[j][k];
+            w.L[i][j] = v * w.il[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < BS; ++i) {                        // y = L^-1 r
+        double v = r[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) v -= w.L[i][k] * w.y[k];
+        w.y[i] = v * w.il[i];
+        q += w.y[i] * w.y[i];
+    }
+    w.dpost = ok ? sgn * 0.5 * log(det) + 0.5 * q : nan("");
+}
+
+// What a committed step needs on top of small_factor: G = S^-1, gr = G r, and xm = L^-T z for the draws.
+template <int B, int BS>
+__device__ __forceinline__ void small_finish(SmallSolve<B>& w, const double (&r)[B], const double* zc, int coord0) {
+#pragma unroll
+    for (int c = 0; c < BS; ++c) {
+        double u[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            double v = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) v -= w.L[i][k] * u[k];
+            u[i] = v * w.il[i];
+        }
+#pragma unroll
+        for (int i = BS - 1; i >= 0; --i) {
+            double v = u[i];
+#pragma unroll
+            for (int k = i + 1; k < BS; ++k) v -= w.L[k][i] * w.G[k][c];
+            w.G[i][c] = v * w.il[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < BS; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < BS; ++k) v += w.G[i][k] * r[k];
+        w.gr[i] = v;
+        w.xm[i] = 0.0;
+    }
+    if (zc) {
+#pragma unroll
+        for (int i = BS - 1; i >= 0; --i) {               // xm = L^-T z_m
+            double v = zc[coord0 + i];
+#pragma unroll
+            for (int k = i + 1; k < BS; ++k) v -= w.L[k][i] * w.xm[k];
+            w.xm[i] = v * w.il[i];
+        }
+    }
+}
+
+template <int B, int NTHR>
+struct FastCtx {
+    static constexpr int NWARP = NTHR / 32;
+    static constexpr int ROWS = 4;              // rows of P per warp per batch
+    static constexpr int PB = B * B + B;        // partial sums per warp: c^T t (B x B) and c^T mu (B)
+    int N, D, NB, ldj, ldp;
+    const double* Jn; const double* hn; const double* J0w; const double* h0w; double J0b, h0b;
+    double* P;
+    double *mu, *xs, *cb, *tb, *part;
+    int *cidx, *slot;
+    int K, tid, lane, warp;
+
+    __device__ __forceinline__ double Jp(int i, int j) const {
+        const int hi = max(i, j), lo = min(i, j);
+        double v = Jn[(size_t)hi * ldj + lo];
+        if (hi < NB) {
+            const int m = hi / B;
+            if (lo / B == m) v += J0w[(size_t)m * B * B + (hi - m * B) * B + (lo - m * B)];
+        } else if (lo == hi) {
+            v += J0b;
+        }
+        return v;
+    }
+    __device__ __forceinline__ double hp(int d) const { return hn[d] + (d < NB ? h0w[d] : h0b); }
+
+    // Evaluate appending coordinates [coord0, coord0+BS): t = P c goes to tb; S (lower triangle of the Schur
+    // complement) and r are returned in every thread.
+    template <int BS>
+    __device__ __forceinline__ void eval_add(int coord0, double (&S)[B][B], double (&r)[B]) {
+#pragma unroll
+        for (int b = 0; b < BS; ++b) {                    // issued early: latency hides behind the pass over P
+#pragma unroll
+            for (int b2 = 0; b2 <= b; ++b2) S[b][b2] = Jp(coord0 + b, coord0 + b2);
+            r[b] = hp(coord0 + b);
+        }
+        for (int e = tid; e < K * BS; e += NTHR) {
+            const int c1 = e / BS, bb = e - c1 * BS;
+            cb[c1 * B + bb] = Jp(cidx[c1], coord0 + bb);
+        }
+        __syncthreads();
+        double ps[BS][BS], pr[BS];
+#pragma unroll
+        for (int b = 0; b < BS; ++b) {
+            pr[b] = 0.0;
+#pragma unroll
+            for (int b2 = 0; b2 < BS; ++b2) ps[b][b2] = 0.0;
+        }
+        for (int r0 = warp * ROWS; r0 < K; r0 += NWARP * ROWS) {
+            double s[ROWS][BS];
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+                for (int b = 0; b < BS; ++b) s[rr][b] = 0.0;
+            for (int c0 = lane; c0 < K; c0 += 128) {
+                double pv[ROWS][4];
+#pragma unroll
+                for (int rr = 0; rr < ROWS; ++rr) {
+                    const double* prow = P + (size_t)min(r0 + rr, K - 1) * ldp;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) pv[rr][u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double* cr = cb + min(c0 + 32 * u, K - 1) * B;
+                    double cv[BS];
+#pragma unroll
+                    for (int b = 0; b < BS; ++b) cv[b] = cr[b];
+#pragma unroll
+                    for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+                        for (int b = 0; b < BS; ++b) s[rr][b] += pv[rr][u] * cv[b];
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) {
+                if (r0 + rr < K) {
+                    const int row = r0 + rr;
+#pragma unroll
+                    for (int b = 0; b < BS; ++b) s[rr][b] = warp_sum(s[rr][b]);
+                    const double m_r = mu[row];
+#pragma unroll
+                    for (int b = 0; b < BS; ++b) {
+                        if (lane == 0) tb[row * B + b] = s[rr][b];
+                        const double cvb = cb[row * B + b];
+                        pr[b] += cvb * m_r;
+#pragma unroll
+                        for (int b2 = 0; b2 < BS; ++b2) ps[b][b2] += cvb * s[rr][b2];
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < BS; ++b) {
+                part[warp * PB + B * B + b] = pr[b];
+#pragma unroll
+                for (int b2 = 0; b2 < BS; ++b2) part[warp * PB + b * B + b2] = ps[b][b2];
+            }
+        }
+        __syncthreads();
+        // block-wide sums of the per-warp partials: lane w holds warp w's, butterfly in a fixed order (deterministic)
+#pragma unroll
+        for (int b = 0; b < BS; ++b) {
+            r[b] -= warp_sum(lane < NWARP ? part[lane * PB + B * B + b] : 0.0);
+#pragma unroll
+            for (int b2 = 0; b2 <= b; ++b2) S[b][b2] -= warp_sum(lane < NWARP ? part[lane * PB + b * B + b2] : 0.0);
+        }
+    }
+
+    // P[r][c] += sgn * (tb[r] G) . tb[c] over the K x K active block; mu (and xs) follow.
+    template <int BS>
+    __device__ __forceinline__ void rank_update(const SmallSolve<B>& w, double sgn, bool draw) {
+        for (int r0 = warp * ROWS; r0 < K; r0 += NWARP * ROWS) {
+            double g[ROWS][BS];
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) {
+                const double* tr = tb + min(r0 + rr, K - 1) * B;
+#pragma unroll
+                for (int k = 0; k < BS; ++k) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int j = 0; j < BS; ++j) v += tr[j] * w.G[j][k];
+                    g[rr][k] = sgn * v;
+                }
+            }
+            for (int c0 = lane; c0 < K; c0 += 128) {
+                double pv[ROWS][4];
+#pragma unroll
+                for (int rr = 0; rr < ROWS; ++rr) {
+                    const double* prow = P + (size_t)min(r0 + rr, K - 1) * ldp;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) pv[rr][u] = (c0 + 32 * u < K) ? prow[c0 + 32 * u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c2 = c0 + 32 * u;
+                    if (c2 < K) {
+                        double tv[BS];
+#pragma unroll
+                        for (int k = 0; k < BS; ++k) tv[k] = tb[c2 * B + k];
+#pragma unroll
+                        for (int rr = 0; rr < ROWS; ++rr) {
+                            if (r0 + rr < K) {
+                                double acc = pv[rr][u];
+#pragma unroll
+                                for (int k = 0; k < BS; ++k) acc += g[rr][k] * tv[k];
+                                P[(size_t)(r0 + rr) * ldp + c2] = acc;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        for (int c1 = tid; c1 < K; c1 += NTHR) {
+            double sm = 0.0, sx = 0.0;
+#pragma unroll
+            for (int k = 0; k < BS; ++k) { sm += tb[c1 * B + k] * w.gr[k]; sx += tb[c1 * B + k] * w.xm[k]; }
+            mu[c1] -= sm;
+            if (draw) xs[c1] -= sx;
+        }
+    }
+
+    // Append the block evaluated by the last eval_add<BS>.
+    template <int BS>
+    __device__ __forceinline__ void commit_add(const SmallSolve<B>& w, int coord0, bool draw) {
+        rank_update<BS>(w, 1.0, draw);
+        for (int e = tid; e < K * BS; e += NTHR) {        // new border rows / columns: -t G
+            const int c1 = e / BS, bb = e - c1 * BS;
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+                double gsel = 0.0;
+#pragma unroll
+                for (int k = 0; k < BS; ++k) gsel = (k == bb) ? w.G[j][k] : gsel;
+                v -= tb[c1 * B + j] * gsel;
+            }
+            P[(size_t)c1 * ldp + K + bb] = v;
+            P[(size_t)(K + bb) * ldp + c1] = v;
+        }
+#pragma unroll
+        for (int b = 0; b < BS; ++b) {
+#pragma unroll
+            for (int b2 = 0; b2 < BS; ++b2)
+                if (tid == 32 + b * BS + b2) P[(size_t)(K + b) * ldp + K + b2] = w.G[b][b2];
+            if (tid == b) {
+                mu[K + b] = w.gr[b];
+                if (draw) xs[K + b] = w.xm[b];
+                cidx[K + b] = coord0 + b;
+            }
+        }
+        __syncthreads();
+        K += BS;
+    }
+
+    // Remove the block at pos (G = P_mm^-1, gr = P_mm^-1 mu_m in w) and move the last block into its place.
+    __device__ __forceinline__ void commit_remove(const SmallSolve<B>& w, int pos) {
+        for (int e = tid; e < K * B; e += NTHR) {         // tb = P[:, pos block] (read as rows: P symmetric)
+            const int bb = e / K, c2 = e - bb * K;
+            tb[c2 * B + bb] = P[(size_t)(pos + bb) * ldp + c2];
+        }
+        __syncthreads();
+        rank_update<B>(w, -1.0, false);                   // P -= t P_mm^-1 t^T,  mu_R -= P_Rm P_mm^-1 mu_m
+        __syncthreads();
+        const int last = K - B;
+        if (pos != last) {
+            for (int e = tid; e < K * B; e += NTHR) {     // rows of the last block -> rows at pos
+                const int bb = e / K, c2 = e - bb * K;
+                P[(size_t)(pos + bb) * ldp + c2] = P[(size_t)(last + bb) * ldp + c2];
+            }
+            __syncthreads();
+            for (int e = tid; e < last * B; e += NTHR) {  // columns of the last block -> columns at pos
+                const int c1 = e / B, bb = e - c1 * B;
+                P[(size_t)c1 * ldp + pos + bb] = P[(size_t)c1 * ldp + last + bb];
+            }
+            if (tid < B) {
+                mu[pos + tid] = mu[last + tid];
+                cidx[pos + tid] = cidx[last + tid];
+            }
+            if (tid == 0) slot[cidx[last] / B] = pos;
+        }
+        __syncthreads();
+        K -= B;
+    }
+};
+
+template <int B, int NTHR>
+size_t fast_smem_bytes(int N) {
+    const int D = N * B + 1, Dpad = (D + 1) & ~1;
+    return ((size_t)2 * Dpad + (size_t)2 * Dpad * B + (size_t)(NTHR / 32) * (B * B + B)) * sizeof(double) +
+           ((size_t)Dpad + N) * sizeof(int);
+}
+
+template <int B, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB)
+spike_slab_fast_kernel(SpikeSlabArgs A) {
+    extern __shared__ __align__(16) double ssm[];
+    const int ln = blockIdx.x;
+    const int N = A.N, D = A.D;
+    const int Dpad = (D + 1) & ~1;
+
+    FastCtx<B, NTHR> c;
+    c.N = N; c.D = D; c.NB = N * B; c.ldj = A.ldj; c.ldp = D;
+    c.Jn = A.J + (size_t)ln * A.stride_n;
+    c.hn = A.h + (size_t)ln * A.ldh;
+    c.J0w = A.J0w + (size_t)ln * N * B * B;
+    c.h0w = A.h0w + (size_t)ln * N * B;
+    c.J0b = A.J0b[ln]; c.h0b = A.h0b[ln];
+    c.P = A.P + (size_t)ln * D * D;
+    double* p = ssm;
+    c.mu = p; p += Dpad;
+    c.xs = p; p += Dpad;
+    c.cb = p; p += (size_t)Dpad * B;
+    c.tb = p; p += (size_t)Dpad * B;
+    c.part = p; p += (size_t)(NTHR / 32) * (B * B + B);
+    c.cidx = reinterpret_cast<int*>(p);
+    c.slot = c.cidx + Dpad;
+    c.tid = threadIdx.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
+    c.K = 0;
+    const int tid = threadIdx.x;
+
+    unsigned char* a = A.a + (size_t)ln * N;
+    const double* cprior = A.cprior + (size_t)ln * N;
+    const double* lrho = A.logit_rho + (size_t)ln * N;
+    const int* perm = A.perm + (size_t)ln * N;
+    const double* us = A.us + (size_t)ln * N;
+    const double* zc = A.z + (size_t)ln * A.ldz;
+
+    for (int m = tid; m < N; m += NTHR) c.slot[m] = -1;
+    __syncthreads();
+
+    // One loop over all steps of the three phases:
+    //   BUILD  P, mu for the current active set: bias first, then the active blocks in ascending order
+    //   SCAN   the collapsed scan over a random permutation (regression.py:286-320)
+    //   DRAW   restart from the empty set and border in ascending coordinate order, bias last, with the normals z:
+    //          step for step the back-substitution x = chol(Jp_SS)^-T z of sample_gaussian; mu + x is the draw and
+    //          the accumulated dpost is _marginal_likelihood (regression.py:343-378).
+    enum { PH_BUILD_BIAS, PH_BUILD, PH_SCAN, PH_DRAW, PH_DONE };
+    int phase = A.do_scan[ln] ? PH_BUILD_BIAS : PH_DRAW;
+    int cursor = 0, fail = 0;
+    double ml = 0.0;
+    SmallSolve<B> w;
+    while (phase != PH_DONE) {
+        int m = -1;
+        bool is_bias = false;
+        if (phase == PH_BUILD_BIAS) {
+            is_bias = true;
+        } else if (phase == PH_BUILD) {
+            while (cursor < N && !a[cursor]) ++cursor;
+            if (cursor == N) { phase = PH_SCAN; cursor = 0; continue; }
+            m = cursor++;
+        } else if (phase == PH_SCAN) {
+            if (cursor == N) { __syncthreads(); phase = PH_DRAW; cursor = 0; c.K = 0; continue; }
+            m = perm[cursor];
+        } else {
+            while (cursor < N && !a[cursor]) ++cursor;
+            if (cursor == N) is_bias = true; else m = cursor++;
+        }
+        const bool scan = (phase == PH_SCAN), draw = (phase == PH_DRAW);
+        const int pos = scan ? c.slot[m] : -1;
+        const int coord0 = is_bias ? D - 1 : m * B;
+        double S[B][B], r[B];
+        if (pos >= 0) {
+            // removal: ml(with) - ml(without) read off P and mu, no pass over P, no barrier
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+#pragma unroll
+                for (int k = 0; k <= i; ++k) S[i][k] = c.P[(size_t)(pos + i) * c.ldp + pos + k];
+                r[i] = c.mu[pos + i];
+            }
+            small_factor<B, B>(w, S, r, 1.0);
+        } else if (is_bias) {
+            c.template eval_add<1>(coord0, S, r);
+            small_factor<B, 1>(w, S, r, -1.0);
+        } else {
+            c.template eval_add<B>(coord0, S, r);
+            small_factor<B, B>(w, S, r, -1.0);
+        }
+        if (!(w.dpost == w.dpost)) { fail = 1; break; }
+        bool do_add = true, do_remove = false;
+        if (scan) {
+            const double lo = w.dpost + cprior[m] + lrho[m];
+            const double p0 = 1.0 / (1.0 + exp(lo));
+            const int v = us[cursor] > p0;
+            if (A.logodds && tid == 0) A.logodds[(size_t)ln * N + cursor] = lo;
+            do_add = (pos < 0) && v;
+            do_remove = (pos >= 0) && !v;
+            ++cursor;
+        } else if (draw) {
+            ml += w.dpost + (is_bias ? 0.5 * log(c.J0b) - 0.5 * c.h0b * c.h0b / c.J0b : cprior[m]);
+        }
+        if (do_add) {
+            if (!is_bias && tid == 0) { c.slot[m] = c.K; a[m] = 1; }
+            if (is_bias) {
+                small_finish<B, 1>(w, r, draw ? zc : nullptr, coord0);
+                c.template commit_add<1>(w, coord0, draw);
+            } else {
+                small_finish<B, B>(w, r, draw ? zc : nullptr, coord0);
+                c.template commit_add<B>(w, coord0, draw);
+            }
+        } else if (do_remove) {
+            small_finish<B, B>(w, r, nullptr, 0);
+            __syncthreads();                              // every thread has read slot[m] before it changes
+            if (tid == 0) { c.slot[m] = -1; a[m] = 0; }
+            c.commit_remove(w, pos);
+        }
+        if (phase == PH_BUILD_BIAS) phase = PH_BUILD;
+        else if (draw && is_bias) phase = PH_DONE;
+    }
+    __syncthreads();
+    double* Wn = A.W + (size_t)ln * N * B;
+    for (int e = tid; e < N * B; e += NTHR) Wn[e] = 0.0;
+    __syncthreads();
+    if (!fail) {
+        for (int k = tid; k < c.K; k += NTHR) {
+            const int d = c.cidx[k];
+            const double v = c.mu[k] + c.xs[k];
+            if (d < N * B) Wn[d] = v; else A.bias[ln] = v;
+        }
+    }
+    if (tid == 0) {
+        if (A.ml) A.ml[ln] = fail ? nan("") : ml;
+        A.status[ln] = fail;
+    }
+}
+
+template <int B, int NTHR, int MINB>
+int launch_fast(const SpikeSlabArgs& A, cudaStream_t stream) {
+    const size_t smem = fast_smem_bytes<B, NTHR>(A.N);
+    if (smem > 227 * 1024) {
+        pyglm_set_error("pyglm_spike_slab_update: N*B=%d too large for the shared-memory state (%zu bytes)", A.N * B, smem);
+        return PYGLM_ERR_INVALID;
+    }
+    PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_fast_kernel<B, NTHR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spike_slab_fast_kernel<B, NTHR, MINB><<<A.n_loc, NTHR, smem, stream>>>(A);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
+template <int B>
+int launch_fast_variant(const SpikeSlabArgs& A, int variant, cudaStream_t stream) {
+    switch (variant) {
+        case 1: return launch_fast<B, 256, 2>(A, stream);
+        case 2: return launch_fast<B, 512, 2>(A, stream);
+        default: return launch_fast<B, 512, 1>(A, stream);
+    }
+}
+
 // perm: Fisher-Yates permutation of 0..N-1 per local neuron; us: N uniforms; z: D normals keyed by coordinate.
 // Streams are keyed by the GLOBAL neuron index so that sharding does not change the draws.
 __global__ void scan_randomness_kernel(int N, int D, int n_loc, int n_off, unsigned long long seed, unsigned call_id,
@@ -514,8 +1010,23 @@ extern "C" int pyglm_spike_slab_update(int N, int B, int n_loc,
     size_t smem = ((size_t)2 * Dpad + (size_t)3 * Dpad * B + 2 * SS_BMAX * SS_BMAX + 3 * SS_BMAX + 8) * sizeof(double)
                 + ((size_t)Dpad + N) * sizeof(int);
     PYGLM_CHECK_ARG(smem <= 227 * 1024, "pyglm_spike_slab_update: N*B=%d too large for the shared-memory state (%zu bytes)", N * B, smem);
-    PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spike_slab_kernel<<<n_loc, SS_THREADS, smem, stream>>>(A);
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("PYGLM_SS_VARIANT"); variant = e ? atoi(e) : 0; }
+    if (B <= 4 && variant < 10) {                        // variant >= 10: force the generic kernel (tests, B > 4)
+        switch (B) {
+            case 1: return launch_fast_variant<1>(A, variant, stream);
+            case 2: return launch_fast_variant<2>(A, variant, stream);
+            case 3: return launch_fast_variant<3>(A, variant, stream);
+            default: return launch_fast_variant<4>(A, variant, stream);
+        }
+    }
+#define SS_LAUNCH(THR, MINB)                                                                                              \
+    do {                                                                                                                   \
+        PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_kernel<THR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        spike_slab_kernel<THR, MINB><<<n_loc, THR, smem, stream>>>(A);                                                      \
+    } while (0)
+    SS_LAUNCH(512, 1);
+#undef SS_LAUNCH
     PYGLM_LAUNCH_CHECK();
     return PYGLM_OK;
 }
