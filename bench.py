@@ -225,13 +225,15 @@ def main():
         tc = "gram_tc_mma" in kern_ms
         if tc:
             # tcgen05 path: S(S+1)/2 int8 digit products per algorithmic MAC (S = 4 -> 10)
-            S = eng.gram_digits
+            plan = ds.buffers[("tc_plan", n_loc)]
+            S = plan.S
             ops = gram_flop * (S * (S + 1) // 2)
             achieved = ops / (kern_ms["gram_tc_mma"] * 1e-3) / 1e12
             peak = 2.0 * pk["bf16_sustained"]
             roof = dict(kernel="gram_tc_kernel (tcgen05 kind::i8, %d radix-256 digits, exact int32/int64 sums)" % S,
                         bound="tensor", achieved=achieved, peak=peak, unit="TOP/s", frac=achieved / peak, traffic=None,
                         algorithmic="N*T*D*(D+1) FP64 flop x %d int8 digit products" % (S * (S + 1) // 2),
+                        max_rel_dev_vs_fp64_kernel=plan.max_rel_dev,
                         peak_source="2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s): int8 runs on the same "
                                     "tcgen05 pipe at twice the bf16 rate; kernel timed inside the sweep" % pk["source"])
         else:

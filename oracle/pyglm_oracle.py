@@ -506,6 +506,27 @@ def tc_digits(scaled, S):
     return out[::-1]
 
 
+def tc_dither(p, t):
+    """Index-keyed dither in (-1/2, 1/2) added before rounding Z to its fixed-point grid (gram_tc.cu: tc_dither)."""
+    with np.errstate(over="ignore"):
+        h = np.asarray(p, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) \
+            + np.asarray(t, dtype=np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
+        h ^= h >> np.uint64(33)
+        h *= np.uint64(0xFF51AFD7ED558CCD)
+        h ^= h >> np.uint64(33)
+        h *= np.uint64(0xC4CEB9FE1A85EC53)
+        h ^= h >> np.uint64(33)
+    return ((h >> np.uint64(40)).astype(np.float64) + 0.5) * 2.0 ** -24 - 0.5
+
+
+def tc_z_digits(Xt, i, j, ex, S):
+    """Digits of Z[:, (i,j)] = Xt[:, i] Xt[:, j] as gram_tc.cu stores them (pair index i(i+1)/2 + j)."""
+    T = Xt.shape[0]
+    p = i * (i + 1) // 2 + j
+    scaled = Xt[:, j] * Xt[:, i] * 2.0 ** (8 * S - ex[i] - ex[j])
+    return tc_digits(scaled + tc_dither(np.full(T, p, dtype=np.uint64), np.arange(T, dtype=np.uint64)), S)
+
+
 def tc_gram_reference(Xt, om, S):
     """Xt (T, D) = [X, 1] >= 0, om (T, n) > 0.  Returns (Jint (n, D(D+1)/2) int64 exact digit sums,
     J (n, D, D) float64 lower triangle) as gram_tc.cu computes them."""
@@ -519,7 +540,7 @@ def tc_gram_reference(Xt, om, S):
     for i in range(D):
         for j in range(i + 1):
             p = i * (i + 1) // 2 + j
-            zd = tc_digits(Xt[:, j] * Xt[:, i] * 2.0 ** (8 * S - ex[i] - ex[j]), S)
+            zd = tc_z_digits(Xt, i, j, ex, S)
             for c in range(n):
                 tot = 0
                 for a in range(S):

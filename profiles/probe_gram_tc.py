@@ -14,6 +14,7 @@ import torch
 sys.path.insert(0, ".")
 from pyglm_b200.kernels import CudaKernels, pad_ldn  # noqa: E402
 from pyglm_b200.utils.basis import cosine_basis  # noqa: E402
+from oracle import pyglm_oracle as ORC  # noqa: E402  (checker only)
 
 
 def exponent(c):
@@ -58,7 +59,7 @@ def check_exact(K, T, N, B, n, S):
     for i in range(D):
         for j in range(i + 1):
             p = i * (i + 1) // 2 + j
-            d = digits(X[:, j] * X[:, i] * 2.0 ** (8 * S - ex[i] - ex[j]), S)
+            d = ORC.tc_z_digits(X, i, j, ex, S)
             zd[p] = d
             for s in range(S):
                 if not np.array_equal(Zs[s, p, :T], (d[s] & 255).astype(np.uint8)):
@@ -132,6 +133,12 @@ def check_vs_fp64(K, T, N, B, n, S, reps=3):
         flops = n * T * D * (D + 1)
         print("  rep %d: slice %.3f ms  mma %.3f ms  finalize %.3f ms   (%.1f algorithmic TFLOP/s)" %
               (r, t[0], t[1], t[2], flops / (sum(t) * 1e-3) / 1e12))
+    for label, arg in (("multicast on ", 0), ("multicast off", -1)):
+        ts = []
+        for r in range(8):
+            ev[0].record(); plan.mma(arg); ev[1].record(); torch.cuda.synchronize()
+            ts.append(ev[0].elapsed_time(ev[1]))
+        print("  mma %s: min %.3f  median %.3f ms" % (label, min(ts), sorted(ts)[len(ts) // 2]))
     ev[0].record(); plan.mma_probe(); ev[1].record(); torch.cuda.synchronize()
     tp = ev[0].elapsed_time(ev[1])
     S_ = plan.S

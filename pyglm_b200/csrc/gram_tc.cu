@@ -8,7 +8,7 @@
 //     Z[t,p]     ~ 2^(ex_i+ex_j-8S) * sum_s 256^(S-1-s) zs[s][p][t]       (scale: product of column bounds of X~)
 //     omega[t,n] ~ 2^(eo_n-8S)      * sum_s 256^(S-1-s) os[s][n][t]       (scale: column maximum of omega)
 // digit 0 unsigned in [0,255] (all operands are >= 0 on this path), digits 1.. signed round-to-nearest in
-// [-128,127], so the dropped tail is zero-mean.  Every digit product zs[a] * os[b] with a+b <= S-1 is one
+// [-128,127], so the dropped tail is zero-mean (Z is rounded with an index-keyed dither, see tc_dither).  Every digit product zs[a] * os[b] with a+b <= S-1 is one
 // tcgen05.mma into the int32 accumulator of "order" g = a+b; sums of at most 16384 time bins stay below 2^31, so
 // each accumulator is EXACT, and orders are recombined as int64 (sum_g acc_g << 8(S-1-g)), added across time chunks
 // with integer atomics (order-independent => bitwise deterministic) and scaled to FP64 once at the end.
@@ -24,6 +24,7 @@
 // Work item = (pair tile, neuron tile, time chunk <= 16384 bins); persistent CTAs stride over the item list.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -81,6 +82,38 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// One lane of a fully active warp, chosen by the hardware.  Issuing through elect.sync (instead of `lane == 0`) lets the
+// compiler treat everything inside as warp-uniform: descriptors stay in uniform registers and every tcgen05.mma is one
+// UTCIMMA, not a per-lane R2UR waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// Multicast form: the box lands at the same shared-memory offset in every CTA of the cluster named in mask, and each
+// of those CTAs gets the complete_tx on its own barrier at the same offset.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -133,10 +166,33 @@ struct TcItems {
     long long Mpad;         // rows per digit plane of Z
     int Npad;               // rows per digit plane of omega
     long long ldj;          // pitch of Jint rows (>= Mpad)
+    int multicast;          // 1: clusters of two CTAs share each Z tile through TMA multicast (needs n_ntiles == 2)
+    int n_ctas;             // CTAs taking part in the item schedule (a multiple of n_ntiles)
     int probe;              // 1: issue-rate probe -- no operand loads, no result atomics (tensor-pipe peak measurement)
 };
 
-template <int S>
+// Item schedule.  CTAs are grouped n_ntiles at a time; in round k group q works on (pair tile, time chunk) number
+// k * n_groups + q and member j of the group takes neuron tile (j + k) mod n_ntiles.  The members of a group stream the
+// SAME Z tiles at the same time (the second reader hits L2, not HBM), and because the neuron tile rotates from round
+// to round every CTA does the same total work even when the last neuron tile is narrower.
+struct TcWork { int mtile, ntile, chunk, valid; };
+__device__ __forceinline__ TcWork tc_work(const TcItems& it, int round) {
+    const int n_groups = it.n_ctas / it.n_ntiles;
+    const int q = blockIdx.x / it.n_ntiles, j = blockIdx.x - q * it.n_ntiles;
+    const long long lin = (long long)round * n_groups + q;           // (chunk, mtile) pair, mtile fastest
+    TcWork w;
+    w.valid = lin < (long long)it.n_mtiles * it.n_chunks;
+    w.mtile = (int)(lin % it.n_mtiles);
+    w.chunk = (int)(lin / it.n_mtiles);
+    w.ntile = (j + round) % it.n_ntiles;
+    return w;
+}
+// neurons (MMA N) of a neuron tile: the last tile may be narrower, in steps of 16
+__device__ __forceinline__ int tc_tile_n(const TcItems& it, int ntile) {
+    return min(it.nt, (it.n_valid - ntile * it.nt + 15) / 16 * 16);
+}
+
+template <int S, bool MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapO,
                long long* __restrict__ Jint, const TcItems it) {
@@ -148,13 +204,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__
     __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 2];
     __shared__ uint32_t tmem_slot;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
+    const int lane = threadIdx.x & 31;
     const uint32_t sbase = (smem_u32(tc_smem) + 1023u) & ~1023u;   // swizzled tiles want 1024-byte alignment
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_STAGES]);
     const uint32_t tfull = smem_u32(&bars[2 * TC_STAGES]), tempty = smem_u32(&bars[2 * TC_STAGES + 1]);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        // with multicast a stage is free only when BOTH CTAs of the cluster have consumed it (the peer writes into it)
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, MC ? 2 : 1); }
         mbar_init(tfull, 1);
         mbar_init(tempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -166,59 +224,71 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();                                  // peer barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    const uint32_t crank = MC ? cluster_ctarank() : 0u;
     const int acc_cols = 512 / S / 16 * 16;                      // column pitch between the S accumulators
 
-    const long long n_items = (long long)it.n_mtiles * it.n_ntiles * it.n_chunks;
-
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0 && !it.probe) {
+        // ------------------------------------------------------------------ TMA producer (one elected lane issues)
+        if (!it.probe) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int ntile = (int)(item % it.n_ntiles);
-                const int mtile = (int)((item / it.n_ntiles) % it.n_mtiles);
-                const int chunk = (int)(item / ((long long)it.n_ntiles * it.n_mtiles));
-                const int kb0 = chunk * it.blocks_per_chunk;
+            for (int round = 0;; ++round) {
+                const TcWork wk = tc_work(it, round);
+                if (!wk.valid) break;
+                const int kb0 = wk.chunk * it.blocks_per_chunk;
                 const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+                const int rowz = wk.mtile * TC_BM, rowo = wk.ntile * it.nt;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                    const uint32_t fb = full0 + 8 * stage;
-                    mbar_expect_tx(fb, stage_tx);
-                    const uint32_t sa = sbase + stage * STAGE;
-                    const uint32_t sb = sa + S * A_SLICE;
+                    if (elect_one()) {
+                        const uint32_t fb = full0 + 8 * stage;
+                        mbar_expect_tx(fb, stage_tx);
+                        const uint32_t sa = sbase + stage * STAGE;
+                        const uint32_t sb = sa + S * A_SLICE;
+                        if (MC) {
+                            // this CTA fetches half of the rows of every Z digit tile and multicasts them to the pair
 #pragma unroll
-                    for (int s = 0; s < S; ++s)
-                        tma_load_2d(sa + s * A_SLICE, &mapZ, kb * TC_BK, (int)(s * it.Mpad + (long long)mtile * TC_BM), fb);
+                            for (int s = 0; s < S; ++s)
+                                tma_load_2d_mc(sa + s * A_SLICE + crank * (A_SLICE / 2), &mapZ, kb * TC_BK,
+                                               (int)(s * it.Mpad) + rowz + (int)crank * (TC_BM / 2), fb, (uint16_t)3);
+                        } else {
 #pragma unroll
-                    for (int s = 0; s < S; ++s)
-                        tma_load_2d(sb + s * B_SLICE, &mapO, kb * TC_BK, s * it.Npad + ntile * it.nt, fb);
+                            for (int s = 0; s < S; ++s)
+                                tma_load_2d(sa + s * A_SLICE, &mapZ, kb * TC_BK, (int)(s * it.Mpad) + rowz, fb);
+                        }
+#pragma unroll
+                        for (int s = 0; s < S; ++s)
+                            tma_load_2d(sb + s * B_SLICE, &mapO, kb * TC_BK, s * it.Npad + rowo, fb);
+                    }
+                    __syncwarp();
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, tphase = 0;
-            uint32_t idesc[2][2];
-            for (int a = 0; a < 2; ++a)
-                for (int b = 0; b < 2; ++b) idesc[a][b] = tc_idesc(a, b, it.nt);
-            for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int chunk = (int)(item / ((long long)it.n_ntiles * it.n_mtiles));
-                const int kb0 = chunk * it.blocks_per_chunk;
-                const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
-                mbar_wait(tempty, tphase ^ 1);           // epilogue has drained the accumulators of the previous item
+        // ------------------------------------------------------------------ MMA issuer (one elected lane issues)
+        int stage = 0;
+        uint32_t phase = 0, tphase = 0;
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int n_mma = tc_tile_n(it, wk.ntile);
+            const uint32_t id_uu = tc_idesc(0, 0, n_mma), id_us = tc_idesc(0, 1, n_mma);
+            const uint32_t id_su = tc_idesc(1, 0, n_mma), id_ss = tc_idesc(1, 1, n_mma);
+            const int kb0 = wk.chunk * it.blocks_per_chunk;
+            const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+            mbar_wait(tempty, tphase ^ 1);               // epilogue has drained the accumulators of the previous item
+            tc_fence_after();
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if (!it.probe) mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    if (!it.probe) mbar_wait(full0 + 8 * stage, phase);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t sa = sbase + stage * STAGE;
-                    const uint32_t sb = sa + S * A_SLICE;
-                    const uint64_t da = tc_smem_desc(sa), db = tc_smem_desc(sb);
+                    const uint64_t da = tc_smem_desc(sa), db = tc_smem_desc(sa + S * A_SLICE);
+                    const uint32_t first = (kb > kb0) ? 1u : 0u;
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {
 #pragma unroll
@@ -228,31 +298,39 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__
                                 const uint64_t adesc = da + (uint64_t)((a * A_SLICE + ks * TC_UK) >> 4);
                                 const uint64_t bdesc = db + (uint64_t)((b * B_SLICE + ks * TC_UK) >> 4);
                                 // first product of order g=a+b in this item overwrites its accumulator
-                                const uint32_t acc = (kb > kb0 || ks > 0 || a > 0) ? 1u : 0u;
-                                tc_mma_i8(tmem + (uint32_t)((a + b) * acc_cols), adesc, bdesc, idesc[a > 0][b > 0], acc);
+                                const uint32_t acc = (ks > 0 || a > 0) ? 1u : first;
+                                const uint32_t idesc = (a > 0) ? ((b > 0) ? id_ss : id_su) : ((b > 0) ? id_us : id_uu);
+                                tc_mma_i8(tmem + (uint32_t)((a + b) * acc_cols), adesc, bdesc, idesc, acc);
                             }
                         }
                     }
-                    if (!it.probe) tc_commit(empty0 + 8 * stage);   // frees the stage once the MMAs above have read it
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (!it.probe) {                      // frees the stage once the MMAs above have read it
+                        if (MC) tc_commit_mc(empty0 + 8 * stage, (uint16_t)3);
+                        else tc_commit(empty0 + 8 * stage);
+                    }
                 }
-                tc_commit(tfull);                         // accumulators of this item complete
-                tphase ^= 1;
+                __syncwarp();
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) tc_commit(tfull);            // accumulators of this item complete
+            __syncwarp();
+            tphase ^= 1;
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may read
         uint32_t tphase = 0;
-        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int ntile = (int)(item % it.n_ntiles);
-            const int mtile = (int)((item / it.n_ntiles) % it.n_mtiles);
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int ntile = wk.ntile, mtile = wk.mtile;
+            const int n_mma = tc_tile_n(it, ntile);
             mbar_wait(tfull, tphase);
             tphase ^= 1;
             tc_fence_after();
             const long long row = (long long)mtile * TC_BM + quarter * 32 + lane;
             const int n0 = ntile * it.nt;
-            for (int c0 = 0; c0 < it.nt; c0 += 16) {
+            for (int c0 = 0; c0 < n_mma; c0 += 16) {
                 int r[S][16];
 #pragma unroll
                 for (int g = 0; g < S; ++g)
@@ -279,6 +357,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();                                  // no CTA leaves while its peer may still signal it
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
@@ -303,6 +382,16 @@ colmax_kernel(const double* __restrict__ A, int ld, long long T, int ncols, long
     }
     if (ng) atomicExch(neg, 1);
     atomicMax(cmax + c, (unsigned long long)__double_as_longlong(m));
+}
+
+// Dither in (-1/2, 1/2) keyed by (pair, time bin): the fixed-point rounding of Z uses round(v + dither), which is
+// unbiased and decorrelates the rounding error from the value -- the filtered spike trains take few distinct values,
+// so plain round-to-nearest would repeat the same error thousands of times.  Values that are already integers in the
+// fixed-point grid are left unchanged (|dither| < 1/2).  Deterministic: a pure function of the indices.
+__host__ __device__ inline double tc_dither(unsigned long long p, unsigned long long t) {
+    unsigned long long h = p * 0x9E3779B97F4A7C15ull + t * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 33; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 33; h *= 0xC4CEB9FE1A85EC53ull; h ^= h >> 33;
+    return ((double)(h >> 40) + 0.5) * (1.0 / 16777216.0) - 0.5;
 }
 
 // S radix-256 digits of round(v): digit 0 (most significant) in [0,255], the others signed in [-128,127]
@@ -351,7 +440,7 @@ zslice_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const 
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 unsigned d[S];
-                tc_digits<S>(xs[jl][tq * 16 + k] * xi[tq * 16 + k] * scale, d);
+                tc_digits<S>(xs[jl][tq * 16 + k] * xi[tq * 16 + k] * scale + tc_dither((unsigned long long)p, (unsigned long long)(tb + tq * 16 + k)), d);
 #pragma unroll
                 for (int s = 0; s < S; ++s) pk[s][k >> 2] |= d[s] << (8 * (k & 3));
             }
@@ -455,25 +544,48 @@ int tc_make_map(CUtensorMap* map, const void* base, long long Tpad, long long ro
     return PYGLM_OK;
 }
 
+template <int S, bool MC>
+int tc_launch_kernel(const CUtensorMap& mz, const CUtensorMap& mo, long long* Jint, const TcItems& sched, int smem,
+                     cudaStream_t stream) {
+    PYGLM_CUDA(cudaFuncSetAttribute(gram_tc_kernel<S, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sched.n_ctas);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = MC ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PYGLM_CUDA(cudaLaunchKernelEx(&cfg, gram_tc_kernel<S, MC>, mz, mo, Jint, sched));
+    return PYGLM_OK;
+}
+
 template <int S>
 int tc_launch(const uint8_t* Zs, const uint8_t* Os, long long* Jint, const TcItems& it, long long Tpad, int max_ctas,
               cudaStream_t stream) {
+    const bool mc = it.multicast && it.n_ntiles == 2;
     CUtensorMap mz, mo;
-    int rc = tc_make_map(&mz, Zs, Tpad, (long long)S * it.Mpad, TC_BM);
+    int rc = tc_make_map(&mz, Zs, Tpad, (long long)S * it.Mpad, mc ? TC_BM / 2 : TC_BM);
     if (rc) return rc;
     rc = tc_make_map(&mo, Os, Tpad, (long long)S * it.Npad, it.nt);
     if (rc) return rc;
     const int smem = TC_STAGES * S * (TC_BM * TC_BK + tc_nt_max(S) * TC_BK) + 1024;
-    PYGLM_CUDA(cudaFuncSetAttribute(gram_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0, sms = 0;
     PYGLM_CUDA(cudaGetDevice(&dev));
     PYGLM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long items = (long long)it.n_mtiles * it.n_ntiles * it.n_chunks;
-    int grid = (int)((items < sms) ? items : sms);
-    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-    gram_tc_kernel<S><<<grid, TC_THREADS, smem, stream>>>(mz, mo, Jint, it);
-    PYGLM_LAUNCH_CHECK();
-    return PYGLM_OK;
+    if (max_ctas > 0 && sms > max_ctas) sms = max_ctas;
+    const long long pairs = (long long)it.n_mtiles * it.n_chunks;       // (pair tile, time chunk) combinations
+    long long groups = sms / it.n_ntiles;
+    if (groups < 1) groups = 1;
+    if (groups > pairs) groups = pairs;
+    TcItems sched = it;
+    sched.n_ctas = (int)groups * it.n_ntiles;
+    return mc ? tc_launch_kernel<S, true>(mz, mo, Jint, sched, smem, stream)
+              : tc_launch_kernel<S, false>(mz, mo, Jint, sched, smem, stream);
 }
 
 }  // namespace
@@ -488,7 +600,7 @@ extern "C" int pyglm_gram_tc_geometry(int D, int n_valid, long long T, int S, lo
     const long long Tpad = (T + TC_BK - 1) / TC_BK * TC_BK;
     const int ntmax = tc_nt_max(S);
     const int n_ntiles = (n_valid + ntmax - 1) / ntmax;
-    const int nt = ((n_valid + n_ntiles - 1) / n_ntiles + 15) / 16 * 16;
+    const int nt = ((n_valid + n_ntiles - 1) / n_ntiles + 15) / 16 * 16;   // the last tile may use fewer (steps of 16)
     const long long n_blocks = Tpad / TC_BK;
     const int max_blocks = TC_KCHUNK / TC_BK;
     int n_chunks = (int)((n_blocks + max_blocks - 1) / max_blocks);
@@ -557,7 +669,8 @@ extern "C" int pyglm_gram_tc_slice_omega(const double* Om, int ldo, long long T,
 }
 
 // The tcgen05 integer GEMM: Jint[n][pair] = sum_t sum_{a+b<S} 256^(S-1-a-b) zs[a][pair][t] os[b][n][t]  (exact).
-// Jint: n_valid rows of pitch ldjint >= Mpad int64, overwritten.  max_ctas <= 0: one CTA per SM.
+// Jint: n_valid rows of pitch ldjint >= Mpad int64, overwritten.  max_ctas == 0: one CTA per SM; > 0 caps the CTA count;
+// < 0 (measurement hook): cluster multicast off, -1 = no cap, -k = cap k.
 static int gram_tc_mma_impl(const unsigned char* Zs, const unsigned char* Os, int D, int n_valid, long long T, int S,
                             long long* Jint, long long ldjint, int max_ctas, int probe, cudaStream_t stream) {
     PYGLM_CHECK_ARG(Zs && Os && Jint, "pyglm_gram_tc_mma: null pointer");
@@ -571,6 +684,10 @@ static int gram_tc_mma_impl(const unsigned char* Zs, const unsigned char* Os, in
     it.M = g[0]; it.Mpad = g[1]; it.Npad = (int)g[3]; it.nt = (int)g[4]; it.n_ntiles = (int)g[5];
     it.n_chunks = (int)g[6]; it.blocks_per_chunk = (int)g[7]; it.n_blocks = (int)(g[2] / TC_BK);
     it.n_mtiles = (int)(g[1] / TC_BM); it.n_valid = n_valid; it.ldj = ldjint; it.probe = probe;
+    static int multicast = -1;
+    if (multicast < 0) { const char* e = getenv("PYGLM_TC_MULTICAST"); multicast = e ? atoi(e) : 1; }
+    it.multicast = multicast; it.n_ctas = 0;
+    if (max_ctas < 0) { it.multicast = 0; max_ctas = (max_ctas == -1) ? 0 : -max_ctas; }   // measurement hook
     PYGLM_CUDA(cudaMemsetAsync(Jint, 0, sizeof(long long) * (size_t)n_valid * (size_t)ldjint, stream));
     switch (S) {
         case 3: return tc_launch<3>(Zs, Os, Jint, it, g[2], max_ctas, stream);

@@ -51,9 +51,10 @@ class DeviceDataset(object):
 
 class GibbsEngine(object):
     def __init__(self, N, B, kernels=None, seed=0, comm=None, shard="neuron", gram="auto", gram_digits=4):
-        """gram: "fp64" = FP64 DMMA kernel (gram.cu); "tc" = tcgen05 integer-digit kernel (gram_tc.cu), error
-        <= 1e-9 relative against FP64; "auto" = "tc" when the design is non-negative, the contraction is large
-        enough to matter and the digit planes of Z fit in HBM, else "fp64"."""
+        """gram: "fp64" = FP64 DMMA kernel (gram.cu); "tc" = tcgen05 integer-digit kernel (gram_tc.cu), checked
+        against the FP64 kernel on the first sweep (<= 5e-10 relative, else one more digit, else FP64);
+        "auto" = "tc" when the design is non-negative, the contraction is large enough to matter and the digit
+        planes of Z fit in HBM, else "fp64".  gram_digits: radix-256 digits the tc path starts with (4 or 5)."""
         assert shard in ("neuron", "time")
         assert gram in ("auto", "fp64", "tc") and gram_digits in (3, 4, 5)
         self.gram_mode, self.gram_digits = gram, gram_digits
@@ -126,31 +127,64 @@ class GibbsEngine(object):
 
     # ------------------------------------------------------------------ Gram dispatch
     TC_MIN_WORK = 2e11          # pairs * T * neurons below which the FP64 kernel is already sub-millisecond
+    TC_ACCEPT = 5e-10           # accepted max relative deviation from the FP64 kernel (stated tolerance 1e-9, 2x margin)
+
+    def _tc_build(self, ds, n, digits):
+        need = gram_tc_bytes(self.D, n, ds.T, digits)
+        free = torch.cuda.mem_get_info(self.K.device)[0]
+        if need >= 0.9 * free:
+            return None
+        try:
+            return self.K.gram_tc_plan(ds.Xp, self.D, n, digits)
+        except ValueError:
+            return None                  # signed design: the digits of Z assume x >= 0
 
     def _tc_plan(self, ds, n):
         """The dataset's tensor-core Gram plan for n local neurons, or None when the FP64 kernel should run."""
-        if self.gram_mode == "fp64":
+        if self.gram_mode == "fp64" or not hasattr(self.K, "gram_tc_plan"):
             return None
-        key = ("tc_plan", n, self.gram_digits)
+        key = ("tc_plan", n)
         if key not in ds.buffers:
-            plan = None
             M = self.D * (self.D + 1) // 2
-            need = gram_tc_bytes(self.D, n, ds.T, self.gram_digits)
             want = self.gram_mode == "tc" or float(M) * ds.T * n >= self.TC_MIN_WORK
-            free = torch.cuda.mem_get_info(self.K.device)[0] if want else 0
-            if want and need < 0.9 * free:
-                try:
-                    plan = self.K.gram_tc_plan(ds.Xp, self.D, n, self.gram_digits)
-                except ValueError:
-                    plan = None          # signed design: digits of Z assume x >= 0
+            plan = self._tc_build(ds, n, self.gram_digits) if want else None
             if plan is None and self.gram_mode == "tc":
-                raise RuntimeError("gram='tc' needs a non-negative design and %.1f GB of free HBM (%.1f GB free)"
-                                   % (need / 1e9, free / 1e9))
+                raise RuntimeError("gram='tc' needs a non-negative design and %.1f GB of free HBM"
+                                   % (gram_tc_bytes(self.D, n, ds.T, self.gram_digits) / 1e9))
             ds.buffers[key] = plan
         return ds.buffers[key]
 
+    def _tc_verified(self, ds, omega, n, plan):
+        """First use of a plan: run it beside the FP64 kernel on the sweep's own omega and keep it only if the
+        two agree to TC_ACCEPT on every lower-triangle entry; otherwise add a digit, then give up (FP64).  The
+        deviation of the integer-digit product depends on the data (sparser trains -> smaller entries relative to
+        the fixed-point scale), so it is measured, not assumed."""
+        key = ("tc_plan", n)
+        J_ref = self.K.weighted_gram(ds.Xp, omega, self.D, n)
+        tril = torch.tril(torch.ones(self.D, self.D, dtype=torch.bool, device=J_ref.device))
+        while plan is not None:
+            J_tc = plan.gram(omega)
+            a, b = J_tc[:, :self.D, :self.D], J_ref[:, :self.D, :self.D]
+            dev = torch.where(tril & (b != 0), (a - b).abs() / b.abs(), torch.zeros_like(b))
+            plan.max_rel_dev = float(dev.max())
+            del J_tc, dev
+            if plan.max_rel_dev <= self.TC_ACCEPT:
+                plan.verified = True
+                break
+            digits = plan.S + 1
+            ds.buffers[key] = plan = None
+            torch.cuda.empty_cache()
+            if digits <= 5:
+                plan = self._tc_build(ds, n, digits)
+        if plan is None and self.gram_mode == "tc":
+            raise RuntimeError("gram='tc': the integer-digit Gram deviates from FP64 by more than %.1e" % self.TC_ACCEPT)
+        ds.buffers[key] = plan
+        return plan
+
     def weighted_gram(self, ds, omega, n, J):
         plan = self._tc_plan(ds, n)
+        if plan is not None and not plan.verified:
+            plan = self._tc_verified(ds, omega, n, plan)
         if plan is not None:
             e0 = self._mark("gram_tc_slice")
             plan.slice_omega(omega)

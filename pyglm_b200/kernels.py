@@ -229,6 +229,7 @@ class TcGramPlan(object):
 
     def __init__(self, K, Xp, D, n_valid, S=4):
         self.K, self.D, self.n, self.S = K, D, n_valid, S
+        self.verified, self.max_rel_dev = False, None      # set by GibbsEngine._tc_verified
         self.T, self.ldx = Xp.shape
         g = K.gram_tc_geometry(D, n_valid, self.T, S)
         self.geom = g

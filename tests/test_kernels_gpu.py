@@ -235,7 +235,7 @@ def test_gram_tc_integer_sums_are_exact(K, T, N, B, n_loc, S):
     Zs = plan.Zs.cpu().numpy()
     ex = [O.tc_exponent(c) for c in Xt.max(0)]
     for (i, j) in [(0, 0), (D - 1, 0), (D - 1, D - 1), (D // 2, D // 3)]:
-        zd = O.tc_digits(Xt[:, j] * Xt[:, i] * 2.0 ** (8 * S - ex[i] - ex[j]), S)
+        zd = O.tc_z_digits(Xt, i, j, ex, S)
         for s in range(S):
             np.testing.assert_array_equal(Zs[s, i * (i + 1) // 2 + j, :T], (zd[s] & 255).astype(np.uint8))
     assert Zs[:, :, T:].max(initial=0) == 0 and Zs[:, g["M"]:].max(initial=0) == 0
@@ -245,8 +245,8 @@ def test_gram_tc_integer_sums_are_exact(K, T, N, B, n_loc, S):
     np.testing.assert_array_equal(np.tril(J[:, :D, :D]), J_ref)
 
 
-@pytest.mark.parametrize("T,N,B,n_loc,S", [(40000, 16, 2, 40, 4), (20000, 10, 2, 200, 4), (5000, 27, 3, 27, 5),
-                                           (60000, 6, 2, 12, 4)])
+@pytest.mark.parametrize("T,N,B,n_loc,S", [(40000, 16, 2, 40, 4), (20000, 10, 2, 200, 5), (5000, 27, 3, 27, 5),
+                                           (60000, 6, 2, 12, 5), (100000, 12, 2, 24, 4)])
 def test_gram_tc_matches_oracle(K, T, N, B, n_loc, S):
     """J from the tensor-core kernel against the oracle's FP64 X^T diag(omega) X (regression.py:251-256): <= 1e-9."""
     Xp, X, om = _tc_inputs(K, T, N, B, n_loc, seed=T + 1)
