@@ -47,6 +47,36 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+def int8_peak():
+    """cuBLASLt int8 GEMM throughput measured on the pool's B200 (profiles/r01b_int8_peak.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01b_int8_peak.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tops=float(d["int8_gemm_8192_tops"]),
+                    source="cuBLASLt int8 GEMM 8192^3 (torch._int_mm), best of 10, measured on B200: "
+                           "profiles/r01b_int8_peak.json (sustained: %.0f)" % d.get("int8_gemm_8192_sustained_tops", 0.0))
+    except Exception:
+        return None
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture
+    (profiles/r01b_ncu_key_metrics.json, same workload), in bytes; None when absent."""
+    p = os.path.join(ROOT, "profiles", "r01b_ncu_key_metrics.json")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    try:
+        with open(p) as f:
+            d = json.load(f)[kernel]
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = d[k].split()
+            tot += float(v) * unit[u]
+        return tot
+    except Exception:
+        return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -229,13 +259,17 @@ def main():
             S = plan.S
             ops = gram_flop * (S * (S + 1) // 2)
             achieved = ops / (kern_ms["gram_tc_mma"] * 1e-3) / 1e12
-            peak = 2.0 * pk["bf16_sustained"]
+            # denominator: cuBLASLt int8 GEMM (torch._int_mm, 8192^3, best of 10) measured on this pool's B200 by
+            # profiles/profile_sweep.py --int8 (MEASURED_PEAKS.json has no int8 figure); else 2 x the bf16 burst figure
+            i8 = int8_peak()
+            peak = i8["tops"] if i8 else 2.0 * pk["bf16_burst"]
             roof = dict(kernel="gram_tc_kernel (tcgen05 kind::i8, %d radix-256 digits, exact int32/int64 sums)" % S,
-                        bound="tensor", achieved=achieved, peak=peak, unit="TOP/s", frac=achieved / peak, traffic=None,
+                        bound="tensor", achieved=achieved, peak=peak, unit="TOP/s", frac=achieved / peak,
+                        traffic=ncu_traffic("gram_tc_kernel"),
                         algorithmic="N*T*D*(D+1) FP64 flop x %d int8 digit products" % (S * (S + 1) // 2),
                         max_rel_dev_vs_fp64_kernel=plan.max_rel_dev,
-                        peak_source="2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s): int8 runs on the same "
-                                    "tcgen05 pipe at twice the bf16 rate; kernel timed inside the sweep" % pk["source"])
+                        peak_source=(i8["source"] if i8 else "2 x bf16_tflops of MEASURED_PEAKS.json (%s): int8 runs on "
+                                     "the same tcgen05 pipe at twice the bf16 rate" % pk["source"]))
         else:
             fp64_peak = float(os.environ.get("PYGLM_FP64_PEAK_TFLOPS", "35.5"))
             roof = dict(kernel="gram_kernel (FP64 DMMA)", bound="tensor", achieved=gram_tflops, peak=fp64_peak,

@@ -14,6 +14,7 @@ ap.add_argument("--N", type=int, default=200)
 ap.add_argument("--B", type=int, default=2)
 ap.add_argument("--T", type=int, default=100000)
 ap.add_argument("--dgemm", action="store_true", help="measure cuBLAS DGEMM / FP64 peak and exit")
+ap.add_argument("--int8", action="store_true", help="measure cuBLASLt int8 GEMM (torch._int_mm) peak and exit")
 args = ap.parse_args()
 
 import torch
@@ -46,6 +47,39 @@ if args.dgemm:
     torch.cuda.synchronize()
     out["dgemm_8192_sustained_tflops"] = reps * 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
     import json
+    print(json.dumps(out))
+    sys.exit(0)
+
+if args.int8:
+    import json
+    out = {}
+    for n in (8192, 16384):
+        a = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda")
+        b = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda").t()   # column-major B (cuBLASLt "TN")
+        try:
+            for _ in range(3):
+                torch._int_mm(a, b)
+            best = 1e9
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                torch._int_mm(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out["int8_gemm_%d_tops" % n] = 2 * n ** 3 / (best * 1e-3) / 1e12
+            reps = 60 if n == 8192 else 12
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            out["int8_gemm_%d_sustained_tops" % n] = reps * 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        except Exception as e:      # noqa: BLE001
+            out["int8_gemm_%d_error" % n] = repr(e)[:200]
     print(json.dumps(out))
     sys.exit(0)
 
