@@ -160,7 +160,9 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gram", default="auto", choices=["auto", "fp64", "tc"])
-    ap.add_argument("--shard", default="neuron", choices=["neuron", "time"])
+    ap.add_argument("--shard", default="auto", choices=["auto", "neuron", "time"],
+                    help="auto: one GPU -> neuron; several -> time (psi / PG / Gram over time slabs, exact int64 "
+                         "reduce-scatter of the Gram partials, then the neuron-sharded scan and the all-gather of W)")
     ap.add_argument("--ref-neurons", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-neurons", type=int, default=1)
@@ -184,6 +186,8 @@ def main():
     from pyglm_b200.models import SparseBernoulliGLM
     from pyglm_b200.utils.basis import cosine_basis
 
+    if args.shard == "auto":
+        args.shard = "time" if world > 1 else "neuron"
     steps = args.steps if args.steps is not None else 10
     warmup = max(3, args.warmup if args.warmup is not None else 3)
     N, B, L, T = cfg["N"], cfg["B"], cfg["L"], cfg["T"]
@@ -281,13 +285,15 @@ def main():
             warmup=warmup, ms_per_step=dev_ms, higher_is_better=True, scaling="strong", vs_baseline=None,
             dtype="f64 (Gram: int8 digits on tcgen05, exact integer sums, <=1e-9 of FP64)" if tc else "f64",
             data="synthetic",
-            config=dict(workload=name, parallelism="%s-sharded x%d" % (eng.shard, world), gram=("tc" if tc else "fp64"),
+            config=dict(workload=name, parallelism=("time-sharded psi/PG/Gram + reduce-scatter of the Gram partials (%s), neuron-sharded scan + "
+                                     "all-gather of (a, W, b), x%d" % ("exact int64" if tc else "FP64", world)
+                                     if eng.shard == "time" and world > 1 else "%s-sharded x%d" % (eng.shard, world)), gram=("tc" if tc else "fp64"),
                         l2="inputs (X 333 MB, omega 205 MB, Z digit planes 32 GB) exceed the 126 MB L2", **cfg),
             e2e=dict(value=1e3 / e2e_ms, unit="sweeps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
             gpu_launches=int(launches),
             roofline=roof,
             kernels_ms=kern_ms,
-            dominant_kernel=max((k for k in kern_ms if not k.startswith("gram_tc_")), key=lambda k: kern_ms[k]),
+            dominant_kernel=max((k for k in kern_ms if not k.startswith("gram_")), key=lambda k: kern_ms[k]),
             pg_roofline=dict(bound="hbm", achieved=pg_bytes / (kern_ms["pg_draw"] * 1e-3) / 1e9, peak=pk["hbm_gbs"],
                              unit="GB/s", frac=pg_bytes / (kern_ms["pg_draw"] * 1e-3) / 1e9 / pk["hbm_gbs"],
                              peak_source=pk["source"]),

@@ -76,6 +76,10 @@ int pyglm_weighted_gram(const double* Xp, int ldx, int T, const double* Om, int 
  *   pyglm_column_max         cmax[c] = max_t A[t,c] (A >= 0), *neg_flag = 1 if any entry is negative
  *   pyglm_gram_tc_build_z    digit planes Zs[S][Mpad][Tpad] of Z[t,(i,j)] = Xp[t,i] Xp[t,j], i >= j, pair index
  *                            i(i+1)/2 + j; once per dataset (Z does not depend on the Gibbs state); Zs zeroed by caller
+ *   pyglm_gram_tc_build_z_slab  the same for a time slab starting at global bin t_off (time-sharded runs): cmax is the
+ *                            maximum over the WHOLE recording (all-reduced by the caller) and the rounding dither is
+ *                            keyed by the global bin, so the digits do not depend on how the time axis is cut
+ *   pyglm_gram_tc_slice_digits  the digit planes of omega for a GIVEN per-neuron scale omax (all-reduced slab maxima)
  *   pyglm_gram_tc_slice_omega  per sweep: omax[n] = max_t Om[t,n] and digit planes Os[S][Npad][Tpad]
  *   pyglm_gram_tc_mma        Jint[n][pair] = sum_t sum_{a+b<S} 256^(S-1-a-b) Zs[a][pair][t] Os[b][n][t]  (exact int64)
  *   pyglm_gram_tc_finalize   J[n][i][j] = Jint[n][pair] * 2^(ex_i + ex_j + eo_n - 8S - 8), lower triangle        */
@@ -84,6 +88,10 @@ int pyglm_column_max(const double* A, int ld, long long T, int ncols, double* cm
                      pyglm_stream_t stream);
 int pyglm_gram_tc_build_z(const double* Xp, int ldx, long long T, int D, const double* cmax, int S,
                           unsigned char* Zs, long long Mpad, long long Tpad, pyglm_stream_t stream);
+int pyglm_gram_tc_build_z_slab(const double* Xp, int ldx, long long T, long long t_off, int D, const double* cmax,
+                               int S, unsigned char* Zs, long long Mpad, long long Tpad, pyglm_stream_t stream);
+int pyglm_gram_tc_slice_digits(const double* Om, int ldo, long long T, int n_valid, int S, const double* omax,
+                               unsigned char* Os, int Npad, long long Tpad, pyglm_stream_t stream);
 int pyglm_gram_tc_slice_omega(const double* Om, int ldo, long long T, int n_valid, int S, double* omax,
                               int* neg_flag, unsigned char* Os, int Npad, long long Tpad, pyglm_stream_t stream);
 int pyglm_gram_tc_mma(const unsigned char* Zs, const unsigned char* Os, int D, int n_valid, long long T, int S,

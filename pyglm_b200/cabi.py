@@ -32,6 +32,8 @@ SIGNATURES = {
     "pyglm_gram_tc_geometry": (c_int, [c_int, c_int, c_ll, c_int, ptr]),
     "pyglm_column_max": (c_int, [ptr, c_int, c_ll, c_int, ptr, ptr, ptr]),
     "pyglm_gram_tc_build_z": (c_int, [ptr, c_int, c_ll, c_int, ptr, c_int, ptr, c_ll, c_ll, ptr]),
+    "pyglm_gram_tc_build_z_slab": (c_int, [ptr, c_int, c_ll, c_ll, c_int, ptr, c_int, ptr, c_ll, c_ll, ptr]),
+    "pyglm_gram_tc_slice_digits": (c_int, [ptr, c_int, c_ll, c_int, c_int, ptr, ptr, c_int, c_ll, ptr]),
     "pyglm_gram_tc_slice_omega": (c_int, [ptr, c_int, c_ll, c_int, c_int, ptr, ptr, ptr, c_int, c_ll, ptr]),
     "pyglm_gram_tc_mma": (c_int, [ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_ll, c_int, ptr]),
     "pyglm_gram_tc_mma_probe": (c_int, [ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_ll, ptr]),

@@ -411,7 +411,7 @@ __device__ __forceinline__ void tc_digits(double scaled, unsigned (&d)[S]) {
 template <int S>
 __global__ void __launch_bounds__(256)
 zslice_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const double* __restrict__ cmax,
-              uint8_t* __restrict__ Zs, long long Mpad, long long Tpad) {
+              uint8_t* __restrict__ Zs, long long Mpad, long long Tpad, long long t_off) {
     const int i = blockIdx.y;
     const int j0 = blockIdx.x * 32;
     if (j0 > i) return;
@@ -440,7 +440,7 @@ zslice_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const 
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 unsigned d[S];
-                tc_digits<S>(xs[jl][tq * 16 + k] * xi[tq * 16 + k] * scale + tc_dither((unsigned long long)p, (unsigned long long)(tb + tq * 16 + k)), d);
+                tc_digits<S>(xs[jl][tq * 16 + k] * xi[tq * 16 + k] * scale + tc_dither((unsigned long long)p, (unsigned long long)(t_off + tb + tq * 16 + k)), d);
 #pragma unroll
                 for (int s = 0; s < S; ++s) pk[s][k >> 2] |= d[s] << (8 * (k & 3));
             }
@@ -630,42 +630,58 @@ extern "C" int pyglm_column_max(const double* A, int ld, long long T, int ncols,
 
 // Digits of Z = X~_i X~_j for every pair i >= j (sweep-invariant; once per dataset).
 //   Xp (T x ldx) padded design, cmax (D doubles) from pyglm_column_max, Zs: S * Mpad * Tpad bytes, ZEROED by the caller.
-extern "C" int pyglm_gram_tc_build_z(const double* Xp, int ldx, long long T, int D, const double* cmax, int S,
-                                     unsigned char* Zs, long long Mpad, long long Tpad, cudaStream_t stream) {
-    PYGLM_CHECK_ARG(Xp && cmax && Zs, "pyglm_gram_tc_build_z: null pointer");
+//   t_off: global index of the slab's first time bin (time-sharded runs).  The rounding dither of a digit is keyed by
+//   (pair, GLOBAL time bin), so with cmax taken over the whole recording the digits -- and therefore the exact integer
+//   sums -- do not depend on how the time axis is cut into slabs.
+extern "C" int pyglm_gram_tc_build_z_slab(const double* Xp, int ldx, long long T, long long t_off, int D, const double* cmax,
+                                          int S, unsigned char* Zs, long long Mpad, long long Tpad, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(Xp && cmax && Zs && t_off >= 0, "pyglm_gram_tc_build_z: null pointer");
     PYGLM_CHECK_ARG(D <= 65535 && Tpad % TC_BK == 0 && Tpad >= T && Mpad >= (long long)D * (D + 1) / 2,
                     "pyglm_gram_tc_build_z: bad geometry");
     long long tb = (Tpad + 127) / 128;
     dim3 grid((D + 31) / 32, D, (unsigned)(tb > 4096 ? 4096 : tb));
     switch (S) {
-        case 3: zslice_kernel<3><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad); break;
-        case 4: zslice_kernel<4><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad); break;
-        case 5: zslice_kernel<5><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad); break;
+        case 3: zslice_kernel<3><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad, t_off); break;
+        case 4: zslice_kernel<4><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad, t_off); break;
+        case 5: zslice_kernel<5><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad, t_off); break;
         default: pyglm_set_error("pyglm_gram_tc_build_z: S=%d unsupported", S); return PYGLM_ERR_INVALID;
     }
     PYGLM_LAUNCH_CHECK();
     return PYGLM_OK;
 }
 
+extern "C" int pyglm_gram_tc_build_z(const double* Xp, int ldx, long long T, int D, const double* cmax, int S,
+                                     unsigned char* Zs, long long Mpad, long long Tpad, cudaStream_t stream) {
+    return pyglm_gram_tc_build_z_slab(Xp, ldx, T, 0, D, cmax, S, Zs, Mpad, Tpad, stream);
+}
+
 // Per sweep: digits of omega (T x ldo, n_valid columns) -> Os (S * Npad * Tpad bytes, rows >= n_valid stay zero:
 // ZEROED once by the caller); omax (n_valid doubles) and neg_flag are overwritten.
-extern "C" int pyglm_gram_tc_slice_omega(const double* Om, int ldo, long long T, int n_valid, int S, double* omax,
-                                         int* neg_flag, unsigned char* Os, int Npad, long long Tpad, cudaStream_t stream) {
-    PYGLM_CHECK_ARG(Om && omax && Os && neg_flag, "pyglm_gram_tc_slice_omega: null pointer");
-    PYGLM_CHECK_ARG(Tpad % TC_BK == 0 && Tpad >= T && Npad >= n_valid, "pyglm_gram_tc_slice_omega: bad geometry");
-    int rc = pyglm_column_max(Om, ldo, T, n_valid, omax, neg_flag, stream);
-    if (rc) return rc;
+// The digit planes alone, with the per-neuron scale given: omax (n_valid doubles, read only) must be >= every entry of
+// the column.  Time-sharded runs all-reduce (max) the slab maxima first so that every rank slices with the same scale.
+extern "C" int pyglm_gram_tc_slice_digits(const double* Om, int ldo, long long T, int n_valid, int S, const double* omax,
+                                          unsigned char* Os, int Npad, long long Tpad, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(Om && omax && Os, "pyglm_gram_tc_slice_digits: null pointer");
+    PYGLM_CHECK_ARG(Tpad % TC_BK == 0 && Tpad >= T && Npad >= n_valid, "pyglm_gram_tc_slice_digits: bad geometry");
     long long gy = (Tpad + 127) / 128;
-    PYGLM_CHECK_ARG(gy <= 65535, "pyglm_gram_tc_slice_omega: T too large for one launch");
+    PYGLM_CHECK_ARG(gy <= 65535, "pyglm_gram_tc_slice_digits: T too large for one launch");
     dim3 grid((n_valid + 31) / 32, (unsigned)gy);
     switch (S) {
         case 3: oslice_kernel<3><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad); break;
         case 4: oslice_kernel<4><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad); break;
         case 5: oslice_kernel<5><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad); break;
-        default: pyglm_set_error("pyglm_gram_tc_slice_omega: S=%d unsupported", S); return PYGLM_ERR_INVALID;
+        default: pyglm_set_error("pyglm_gram_tc_slice_digits: S=%d unsupported", S); return PYGLM_ERR_INVALID;
     }
     PYGLM_LAUNCH_CHECK();
     return PYGLM_OK;
+}
+
+extern "C" int pyglm_gram_tc_slice_omega(const double* Om, int ldo, long long T, int n_valid, int S, double* omax,
+                                         int* neg_flag, unsigned char* Os, int Npad, long long Tpad, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(Om && omax && Os && neg_flag, "pyglm_gram_tc_slice_omega: null pointer");
+    int rc = pyglm_column_max(Om, ldo, T, n_valid, omax, neg_flag, stream);
+    if (rc) return rc;
+    return pyglm_gram_tc_slice_digits(Om, ldo, T, n_valid, S, omax, Os, Npad, Tpad, stream);
 }
 
 // The tcgen05 integer GEMM: Jint[n][pair] = sum_t sum_{a+b<S} 256^(S-1-a-b) zs[a][pair][t] os[b][n][t]  (exact).

@@ -70,6 +70,16 @@ class Comm(object):
             dist.all_reduce(t, group=self.group)
         return t
 
+    def all_reduce_max(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_reduce_min(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return t
+
     def broadcast_object(self, obj, src=0):
         if self.world == 1:
             return obj

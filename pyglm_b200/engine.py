@@ -82,6 +82,9 @@ class GibbsEngine(object):
         # Optional per-phase device timing: set to {} and every sweep appends (start, end) CUDA-event pairs per
         # phase name; phase_ms() averages them.  Events are recorded on the launching stream.
         self.profile = None
+        # Software pipelining of consecutive sweeps (see sweep()); the pre-launched Gram of the next sweep.
+        self.pipeline = True
+        self._pending = None
 
     def _mark(self, name, start=None):
         if self.profile is None:
@@ -129,12 +132,30 @@ class GibbsEngine(object):
     TC_MIN_WORK = 2e11          # pairs * T * neurons below which the FP64 kernel is already sub-millisecond
     TC_ACCEPT = 5e-10           # accepted max relative deviation from the FP64 kernel (stated tolerance 1e-9, 2x margin)
 
+    def _time_sharded(self):
+        return self.shard == "time" and self.comm.world > 1
+
+    def _agree(self, ok):
+        """Time-sharded ranks take the Gram path decisions together (the reduce-scatter that follows must see the
+        same dtype and shape on every rank): a choice holds only if it holds everywhere."""
+        if not self._time_sharded():
+            return bool(ok)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.K.device)
+        return bool(self.comm.all_reduce_min(flag).item())
+
     def _tc_build(self, ds, n, digits):
         need = gram_tc_bytes(self.D, n, ds.T, digits)
         free = torch.cuda.mem_get_info(self.K.device)[0]
-        if need >= 0.9 * free:
+        if not self._agree(need < 0.9 * free):
             return None
         try:
+            if self._time_sharded():
+                plan = self.K.gram_tc_plan(ds.Xp, self.D, n, digits, comm=self.comm, t_off=ds.t_off)
+                # Jint with the row padding the reduce-scatter over the neuron axis needs (extra rows stay zero)
+                rows = self.comm.world * self.n_max
+                if rows != n:
+                    plan.Jint = torch.zeros(rows, plan.geom["Mpad"], dtype=torch.int64, device=self.K.device)
+                return plan
             return self.K.gram_tc_plan(ds.Xp, self.D, n, digits)
         except ValueError:
             return None                  # signed design: the digits of Z assume x >= 0
@@ -146,7 +167,8 @@ class GibbsEngine(object):
         key = ("tc_plan", n)
         if key not in ds.buffers:
             M = self.D * (self.D + 1) // 2
-            want = self.gram_mode == "tc" or float(M) * ds.T * n >= self.TC_MIN_WORK
+            T_eff = ds.T_global / self.comm.world if self._time_sharded() else ds.T
+            want = self.gram_mode == "tc" or float(M) * T_eff * n >= self.TC_MIN_WORK
             plan = self._tc_build(ds, n, self.gram_digits) if want else None
             if plan is None and self.gram_mode == "tc":
                 raise RuntimeError("gram='tc' needs a non-negative design and %.1f GB of free HBM"
@@ -158,15 +180,21 @@ class GibbsEngine(object):
         """First use of a plan: run it beside the FP64 kernel on the sweep's own omega and keep it only if the
         two agree to TC_ACCEPT on every lower-triangle entry; otherwise add a digit, then give up (FP64).  The
         deviation of the integer-digit product depends on the data (sparser trains -> smaller entries relative to
-        the fixed-point scale), so it is measured, not assumed."""
+        the fixed-point scale), so it is measured, not assumed.  Time-sharded: what is compared are the COMPLETE
+        Grams of each rank's neuron block after the reduce-scatter (the integer totals are the single-GPU ones, so
+        the decision is too); the worst rank decides for all."""
         key = ("tc_plan", n)
-        J_ref = self.K.weighted_gram(ds.Xp, omega, self.D, n)
+        rows = max(self.scan_hi - self.scan_lo, 1) if self._time_sharded() else n
+        J_ref = self._gram_fp64(ds, omega, n, self.K.zeros(rows, self.ldx, self.ldx))
         tril = torch.tril(torch.ones(self.D, self.D, dtype=torch.bool, device=J_ref.device))
         while plan is not None:
-            J_tc = plan.gram(omega)
+            J_tc = self._gram_tc(plan, omega, self.K.zeros(rows, self.ldx, self.ldx))
             a, b = J_tc[:, :self.D, :self.D], J_ref[:, :self.D, :self.D]
             dev = torch.where(tril & (b != 0), (a - b).abs() / b.abs(), torch.zeros_like(b))
-            plan.max_rel_dev = float(dev.max())
+            worst = dev.max().reshape(1)
+            if self._time_sharded():
+                self.comm.all_reduce_max(worst)
+            plan.max_rel_dev = float(worst)
             del J_tc, dev
             if plan.max_rel_dev <= self.TC_ACCEPT:
                 plan.verified = True
@@ -181,21 +209,46 @@ class GibbsEngine(object):
         ds.buffers[key] = plan
         return plan
 
+    def _gram_tc(self, plan, omega, J):
+        e0 = self._mark("gram_tc_slice")
+        plan.slice_omega(omega)
+        e1 = self._mark("gram_tc_slice", e0)
+        plan.mma()
+        e2 = self._mark("gram_tc_mma", e1)
+        if self._time_sharded():
+            nS = self.scan_hi - self.scan_lo
+            Jloc = self.comm.reduce_scatter_rows(plan.Jint)
+            e2 = self._mark("gram_reduce_scatter", e2)
+            if nS > 0:
+                plan.finalize(J, Jint=Jloc[:nS], omax=plan.omax[self.scan_lo:self.scan_hi])
+        else:
+            plan.finalize(J)
+        self._mark("gram_tc_finalize", e2)
+        return J
+
+    def _gram_fp64(self, ds, omega, n, J):
+        if self._time_sharded():
+            Jp = self._wsbuf("J_partial", (self.comm.world * self.n_max, self.ldx, self.ldx), zero=True)
+            self.K.weighted_gram(ds.Xp, omega, self.D, n, J=Jp)
+            e0 = self._mark("gram_reduce_scatter")
+            Jloc = self.comm.reduce_scatter_rows(Jp)
+            self._mark("gram_reduce_scatter", e0)
+            J.copy_(Jloc[:J.shape[0]])
+        else:
+            self.K.weighted_gram(ds.Xp, omega, self.D, n, J=J)
+        return J
+
     def weighted_gram(self, ds, omega, n, J):
+        """J (rows of the scan block) = this dataset's weighted Gram.  Neuron-sharded / single GPU: n = local
+        neurons, J has n rows.  Time-sharded: n = N, the slab's partial sums of ALL neurons are reduce-scattered
+        over the neuron axis (exact int64 sums on the tensor-core path, FP64 otherwise) and J receives the complete
+        Grams of this rank's neuron block."""
         plan = self._tc_plan(ds, n)
         if plan is not None and not plan.verified:
             plan = self._tc_verified(ds, omega, n, plan)
         if plan is not None:
-            e0 = self._mark("gram_tc_slice")
-            plan.slice_omega(omega)
-            e1 = self._mark("gram_tc_slice", e0)
-            plan.mma()
-            e2 = self._mark("gram_tc_mma", e1)
-            plan.finalize(J)
-            self._mark("gram_tc_finalize", e2)
-        else:
-            self.K.weighted_gram(ds.Xp, omega, self.D, n, J=J)
-        return J
+            return self._gram_tc(plan, omega, J)
+        return self._gram_fp64(ds, omega, n, J)
 
     # ------------------------------------------------------------------ coefficients
     def build_Wt(self, A, W, b, lo, hi):
@@ -208,6 +261,17 @@ class GibbsEngine(object):
         Wt[NB, :n] = b[lo:hi]
         self.h2d_bytes += Wt.nbytes
         return self.K.to_device(Wt)
+
+    def build_Wt_device(self, state, lo, hi):
+        """The same from the device copy of the new state (rows [a (N) | W (N*B) | b | status] per neuron), so the
+        next sweep's psi / PG / Gram can be enqueued without a host round trip."""
+        n = hi - lo
+        N, NB = self.N, self.N * self.B
+        Wt = self._wsbuf("Wt", (self.ldx, pad_ldn(n)), zero=True)
+        rows = state[lo:hi]
+        Wt[:NB, :n] = (rows[:, :N].unsqueeze(-1) * rows[:, N:N + NB].reshape(n, N, self.B)).reshape(n, NB).t()
+        Wt[NB, :n] = rows[:, N + NB]
+        return Wt
 
     # ------------------------------------------------------------------ sweep-invariant h
     def _h_lkhd(self, ds, lo, hi):
@@ -222,51 +286,108 @@ class GibbsEngine(object):
         return ds.h_cache[key]
 
     # ------------------------------------------------------------------ the sweep
+    def _augment(self, datasets, Wt, call_base):
+        """psi -> omega ~ PG(1, psi) -> J for the scan block, for every dataset (regression.py:496-508, :225-262).
+        Everything is enqueued on the current stream; nothing here waits for the device."""
+        K, N, D, ldx = self.K, self.N, self.D, self.ldx
+        p_lo, p_hi = self.psi_lo, self.psi_hi
+        nP, nS = p_hi - p_lo, self.scan_hi - self.scan_lo
+        ldn = Wt.shape[1]
+        J = self._wsbuf("J", (max(nS, 1) if self._time_sharded() else nP, ldx, ldx), zero=True)
+        for di, ds in enumerate(datasets):
+            psi = self._buf(ds, "psi", (ds.T, ldn))
+            omega = self._buf(ds, "omega", (ds.T, ldn), zero=True)
+            e0 = self._mark("activation")
+            K.activation(ds.Xp, Wt, D, nP, out=psi)
+            e1 = self._mark("activation", e0)
+            if self.inject is None:
+                K.pg_draw(psi, nP, omega, self.seed, call_base + di, ds.t_off, p_lo, N)
+            else:
+                om = np.asarray(self.inject["omega"][di])[ds.t_off:ds.t_off + ds.T, p_lo:p_hi]
+                omega[:, :nP] = K.to_device(om)
+            e2 = self._mark("pg_draw", e1)
+            if di == 0:
+                self.weighted_gram(ds, omega, nP, J)
+            else:
+                Jd = self._wsbuf("J_extra", tuple(J.shape), zero=True)
+                self.weighted_gram(ds, omega, nP, Jd)
+                J += Jd
+            self._mark("weighted_gram", e2)
+        self._aug_end = self._mark("idle_before_scan")        # start of the gap until the scan kernel is enqueued
+        return J[:nS] if self._time_sharded() else J
+
+    def _prelaunched(self, datasets, A, W, b):
+        """The Gram enqueued at the end of the previous sweep, if it was computed from exactly this state and these
+        datasets (users may edit regressions[n].a / .W / .b or swap data between sweeps: then it is discarded)."""
+        pend, self._pending = self._pending, None
+        if pend is None or self.inject is not None:
+            return None
+        ds_ids, A0, W0, b0, J = pend
+        if ds_ids != [id(ds) for ds in datasets]:
+            return None
+        if not (np.array_equal(A0, A) and np.array_equal(W0, W) and np.array_equal(b0, b)):
+            return None
+        return J
+
+    def _pinned(self, name, shape, dtype):
+        key = ("pinned", name, tuple(shape), dtype)
+        if key not in self._ws:
+            self._ws[key] = torch.empty(*shape, dtype=dtype, pin_memory=(self.K.device.type == "cuda"))
+        return self._ws[key]
+
+    def _upload_priors(self, pr, a_host, do_scan):
+        """One pinned staging buffer and one asynchronous copy for all prior terms of the scan block (and one for the
+        two byte arrays) instead of eight pageable, stream-synchronising copies."""
+        K = self.K
+        names = ("J0w", "h0w", "J0b", "h0b", "cprior", "logit_rho")
+        sizes = [pr[k].size for k in names]
+        stage = self._pinned("prior", (sum(sizes),), torch.float64)
+        host = stage.numpy()
+        off = 0
+        for k, sz in zip(names, sizes):
+            host[off:off + sz] = pr[k].ravel()
+            off += sz
+        dev = self._wsbuf("prior_dev", (sum(sizes),))
+        dev.copy_(stage, non_blocking=True)
+        out, off = {}, 0
+        for k, sz in zip(names, sizes):
+            out[k] = dev[off:off + sz].view(pr[k].shape)
+            off += sz
+        nb = a_host.size + do_scan.size
+        bstage = self._pinned("prior_bytes", (nb,), torch.uint8)
+        bh = bstage.numpy()
+        bh[:a_host.size] = a_host.ravel()
+        bh[a_host.size:] = do_scan.astype(np.uint8)
+        bdev = self._wsbuf("prior_bytes_dev", (nb,), dtype=torch.uint8)
+        bdev.copy_(bstage, non_blocking=True)
+        self.h2d_bytes += stage.numel() * 8 + nb
+        return out, bdev[:a_host.size].view(a_host.shape), bdev[a_host.size:]
+
     def sweep(self, datasets, A, W, b, hypers):
         """One resample_regressions() (models.py:169-171) for all neurons.
         A (N,N) bool, W (N,N,B), b (N,) host state;  hypers: dict rho (N,N), mu_w (N,N,B), S_w (N,N,B,B),
-        mu_b (N,), S_b (N,) host arrays, row n = regression n.  Returns new host (A, W, b)."""
+        mu_b (N,), S_b (N,) host arrays, row n = regression n.  Returns new host (A, W, b).
+
+        Sweeps are software-pipelined: psi / PG / Gram depend only on (a, W, b), not on the hyper-parameters, so as
+        soon as the scan of sweep k has produced the new state on the device the augmentation of sweep k+1 is
+        enqueued behind it, and the host part (D2H of the state, network step, prior terms) overlaps with it."""
         K, N, B, D, ldx = self.K, self.N, self.B, self.D, self.ldx
         comm = self.comm
         p_lo, p_hi = self.psi_lo, self.psi_hi
         s_lo, s_hi = self.scan_lo, self.scan_hi
         nP, nS = p_hi - p_lo, s_hi - s_lo
+        NB = N * B
         self.calls += 1
         call_base = self.calls * 64
 
         J_S = h_S = None
-        if nP > 0 and datasets:
-            Wt = self.build_Wt(A, W, b, p_lo, p_hi)
-            ldn = Wt.shape[1]
-            J = self._wsbuf("J", (nP, ldx, ldx), zero=True)
-            for di, ds in enumerate(datasets):
-                psi = self._buf(ds, "psi", (ds.T, ldn))
-                omega = self._buf(ds, "omega", (ds.T, ldn), zero=True)
-                e0 = self._mark("activation")
-                K.activation(ds.Xp, Wt, D, nP, out=psi)
-                e1 = self._mark("activation", e0)
-                if self.inject is None:
-                    K.pg_draw(psi, nP, omega, self.seed, call_base + di, ds.t_off, p_lo, N)
-                else:
-                    om = np.asarray(self.inject["omega"][di])[ds.t_off:ds.t_off + ds.T, p_lo:p_hi]
-                    omega[:, :nP] = K.to_device(om)
-                e2 = self._mark("pg_draw", e1)
-                if di == 0:
-                    self.weighted_gram(ds, omega, nP, J)
-                else:
-                    Jd = self._wsbuf("J_extra", (nP, ldx, ldx), zero=True)
-                    self.weighted_gram(ds, omega, nP, Jd)
-                    J += Jd
-                self._mark("weighted_gram", e2)
-            if self.shard == "time" and comm.world > 1:
-                # partial Grams of ALL neurons over the local time slab -> complete Grams of the local block
-                Jpad = J
-                if N != comm.world * self.n_max:
-                    Jpad = self._wsbuf("J_pad", (comm.world * self.n_max, ldx, ldx), zero=True)
-                    Jpad[:N] = J
-                J_S = comm.reduce_scatter_rows(Jpad)[:nS]
-            else:
-                J_S = J
+        if datasets:
+            J_S = self._prelaunched(datasets, A, W, b)
+            if J_S is None and nP > 0:
+                J_S = self._augment(datasets, self.build_Wt(A, W, b, p_lo, p_hi), call_base)
+        # new state rows [a (N) | W (N*B) | b | status], one row per neuron of the scan block (padded to n_max)
+        width = N + NB + 2
+        state = K.zeros(self.n_max if comm.world > 1 else nS, width)
         if nS > 0 and datasets:
             h_S = self._h_for_scan(datasets)
             pr = prior_arrays(hypers["rho"][s_lo:s_hi], hypers["mu_w"][s_lo:s_hi], hypers["S_w"][s_lo:s_hi],
@@ -276,9 +397,7 @@ class GibbsEngine(object):
             # deterministic sparsity: a = round(rho) (regression.py:274-275)
             det = ~do_scan
             a_host[det] = np.round(hypers["rho"][s_lo:s_hi][det]).astype(np.uint8)
-            prior = {k: K.to_device(v) for k, v in pr.items()}
-            self.h2d_bytes += sum(v.nbytes for v in pr.values()) + a_host.nbytes + do_scan.size
-            a_dev = K.to_device(a_host)
+            prior, a_dev, do_scan_dev = self._upload_priors(pr, a_host, do_scan)
             if self.inject is None:
                 perm, us, z = K.scan_randomness(N, B, nS, s_lo, self.seed, call_base + 63)
             else:
@@ -287,34 +406,48 @@ class GibbsEngine(object):
                 z = K.to_device(np.asarray(self.inject["z"][s_lo:s_hi], dtype=np.float64))
             P_ws = self._wsbuf("P", (nS * D * D,))
             e3 = self._mark("spike_slab")
-            W_new, b_new, _, _, status = K.spike_slab_update(N, B, J_S, h_S, prior, perm, us, z,
-                                                             K.to_device(do_scan.astype(np.uint8)), a_dev, P_ws=P_ws)
-            self._mark("spike_slab", e3)
-        else:
-            a_dev = K.zeros(0, N, dtype=torch.uint8)
-            W_new, b_new = K.zeros(0, N, B), K.zeros(0)
-            status = K.zeros(0, dtype=torch.int32)
-        # exchange: all-gather the new rows (the only collective of the neuron-sharded sweep)
+            if e3 is not None and getattr(self, "_aug_end", None) is not None:
+                self.profile.setdefault("idle_before_scan", []).append((self._aug_end, e3))
+                self._aug_end = None
+            W_new, b_new, _, _, status = K.spike_slab_update(N, B, J_S, h_S, prior, perm, us, z, do_scan_dev, a_dev,
+                                                             P_ws=P_ws)
+            e4 = self._mark("spike_slab", e3)
+            state[:nS, :N] = a_dev
+            state[:nS, N:N + NB] = W_new.reshape(nS, NB)
+            state[:nS, N + NB] = b_new
+            state[:nS, N + NB + 1] = status
+        # exchange: ONE all-gather of the new rows (the only collective of the neuron-sharded sweep)
         if comm.world > 1:
-            pad = self.n_max - nS
-            if pad:
-                a_dev = torch.cat([a_dev, K.zeros(pad, N, dtype=torch.uint8)])
-                W_new = torch.cat([W_new, K.zeros(pad, N, B)])
-                b_new = torch.cat([b_new, K.zeros(pad)])
-                status = torch.cat([status, K.zeros(pad, dtype=torch.int32)])
-            a_dev = comm.all_gather_rows(a_dev)[:N]
-            W_new = comm.all_gather_rows(W_new)[:N]
-            b_new = comm.all_gather_rows(b_new)[:N]
-            status = comm.all_gather_rows(status)[:N]
-        A_out = a_dev.cpu().numpy().astype(bool)
-        W_out = W_new.cpu().numpy()
-        b_out = b_new.cpu().numpy()
-        st = status.cpu().numpy()
-        self.d2h_bytes += A_out.size + W_out.nbytes + b_out.nbytes + st.nbytes
+            state = comm.all_gather_rows(state)[:N]
+        # state -> host through pinned memory, asynchronously ...
+        stage = self._pinned("state", tuple(state.shape), torch.float64)
+        stage.copy_(state, non_blocking=True)
+        done = None
+        if K.device.type == "cuda":
+            done = torch.cuda.Event()
+            done.record()
+        # ... while the device already starts on the next sweep's psi / PG / Gram
+        pend_J = None
+        if self.pipeline and self.inject is None and datasets and nP > 0 and state.shape[0] == N:
+            Wt_next = self.build_Wt_device(state, p_lo, p_hi)
+            if nS > 0 and datasets:
+                self._mark("exchange", e4)
+            pend_J = self._augment(datasets, Wt_next, call_base + 64)
+        if done is not None:
+            done.synchronize()
+        host = stage.numpy()
+        self.d2h_bytes += host.nbytes
+        A_out = host[:, :N] != 0
+        W_out = host[:, N:N + NB].reshape(-1, N, B).copy()
+        b_out = host[:, N + NB].copy()
+        st = host[:, N + NB + 1]
         if st.any():
+            self._pending = None
             bad = np.nonzero(st)[0]
             raise FloatingPointError("spike-and-slab update lost positive definiteness for neuron(s) %s "
                                      "(ill-conditioned posterior precision)" % bad[:8].tolist())
+        if pend_J is not None:
+            self._pending = ([id(ds) for ds in datasets], A_out, W_out, b_out, pend_J)
         return A_out, W_out, b_out
 
     def _h_for_scan(self, datasets):

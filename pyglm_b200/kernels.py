@@ -179,10 +179,11 @@ class CudaKernels(object):
         self._call("pyglm_column_max", self._p(A), ld, T, ncols, self._p(cmax), self._p(neg), self._stream())
         return cmax, bool(neg.item())
 
-    def gram_tc_plan(self, Xp, D, n_valid, S=4):
+    def gram_tc_plan(self, Xp, D, n_valid, S=4, comm=None, t_off=0):
         """Build the sweep-invariant digit planes of Z = X~_i X~_j (once per dataset) and allocate the per-sweep
-        buffers of the tensor-core Gram.  Raises ValueError when the design has negative entries."""
-        return TcGramPlan(self, Xp, D, n_valid, S)
+        buffers of the tensor-core Gram.  Raises ValueError when the design has negative entries.  comm / t_off:
+        time-sharded runs (Xp is the slab starting at global bin t_off; scales are all-reduced over `comm`)."""
+        return TcGramPlan(self, Xp, D, n_valid, S, comm=comm, t_off=t_off)
 
     # ------------------------------------------------------------------ (4) spike and slab
     def scan_randomness(self, N, B, n_loc, n_off, seed, call_id):
@@ -225,29 +226,45 @@ def gram_tc_bytes(D, n_valid, T, S=4):
 
 class TcGramPlan(object):
     """Resident state of the tcgen05 Gram for one dataset: Zs (S, Mpad, Tpad) uint8 digit planes of the
-    Khatri-Rao operand (built once), Os (S, Npad, Tpad) digit planes of omega and Jint (n, Mpad) int64 (per sweep)."""
+    Khatri-Rao operand (built once), Os (S, Npad, Tpad) digit planes of omega and Jint (n, Mpad) int64 (per sweep).
 
-    def __init__(self, K, Xp, D, n_valid, S=4):
+    Time-sharded runs pass `comm` and the slab's global offset `t_off`: the fixed-point scales (column maxima of X
+    and of omega) are all-reduced (max) over the ranks and the rounding dither is keyed by the global time bin, so
+    the integer partial sums of the slabs add up -- exactly, in int64 -- to the Jint a single GPU would compute."""
+
+    def __init__(self, K, Xp, D, n_valid, S=4, comm=None, t_off=0):
         self.K, self.D, self.n, self.S = K, D, n_valid, S
+        self.comm = comm if (comm is not None and comm.world > 1) else None
         self.verified, self.max_rel_dev = False, None      # set by GibbsEngine._tc_verified
         self.T, self.ldx = Xp.shape
         g = K.gram_tc_geometry(D, n_valid, self.T, S)
         self.geom = g
-        self.cmax, neg = K.column_max(Xp, D)
-        if neg:
+        self.cmax = K.empty(D)
+        self.neg = K.empty(1, dtype=torch.int32)
+        K._call("pyglm_column_max", K._p(Xp), self.ldx, self.T, D, K._p(self.cmax), K._p(self.neg), K._stream())
+        if self.comm is not None:
+            self.comm.all_reduce_max(self.cmax)
+            self.comm.all_reduce_max(self.neg)
+        if bool(self.neg.item()):
             raise ValueError("tensor-core Gram needs a non-negative design matrix")
         self.Zs = torch.zeros(S, g["Mpad"], g["Tpad"], dtype=torch.uint8, device=K.device)
-        K._call("pyglm_gram_tc_build_z", K._p(Xp), self.ldx, self.T, D, K._p(self.cmax), S, K._p(self.Zs),
-                g["Mpad"], g["Tpad"], K._stream())
+        K._call("pyglm_gram_tc_build_z_slab", K._p(Xp), self.ldx, self.T, int(t_off), D, K._p(self.cmax), S,
+                K._p(self.Zs), g["Mpad"], g["Tpad"], K._stream())
         self.Os = torch.zeros(S, g["Npad"], g["Tpad"], dtype=torch.uint8, device=K.device)
         self.omax = K.empty(n_valid)
-        self.neg = K.empty(1, dtype=torch.int32)
         self.Jint = K.empty(n_valid, g["Mpad"], dtype=torch.int64)
 
     def slice_omega(self, Om):
         K, g = self.K, self.geom
-        K._call("pyglm_gram_tc_slice_omega", K._p(Om), Om.shape[1], self.T, self.n, self.S, K._p(self.omax),
-                K._p(self.neg), K._p(self.Os), g["Npad"], g["Tpad"], K._stream(), launches=2)
+        if self.comm is None:
+            K._call("pyglm_gram_tc_slice_omega", K._p(Om), Om.shape[1], self.T, self.n, self.S, K._p(self.omax),
+                    K._p(self.neg), K._p(self.Os), g["Npad"], g["Tpad"], K._stream(), launches=2)
+            return
+        K._call("pyglm_column_max", K._p(Om), Om.shape[1], self.T, self.n, K._p(self.omax), K._p(self.neg),
+                K._stream())
+        self.comm.all_reduce_max(self.omax)
+        K._call("pyglm_gram_tc_slice_digits", K._p(Om), Om.shape[1], self.T, self.n, self.S, K._p(self.omax),
+                K._p(self.Os), g["Npad"], g["Tpad"], K._stream())
 
     def mma(self, max_ctas=0):
         K, g = self.K, self.geom
@@ -261,10 +278,16 @@ class TcGramPlan(object):
         K._call("pyglm_gram_tc_mma_probe", K._p(self.Zs), K._p(self.Os), self.D, self.n, self.T, self.S,
                 K._p(self.Jint), g["Mpad"], K._stream())
 
-    def finalize(self, J):
+    def finalize(self, J, Jint=None, omax=None):
+        """J[n] (FP64, lower triangle) from the integer sums; Jint / omax default to the plan's own (all n neurons),
+        or are the rows a reduce-scatter handed this rank together with the matching slice of omax."""
         K, g = self.K, self.geom
-        K._call("pyglm_gram_tc_finalize", K._p(self.Jint), g["Mpad"], K._p(self.cmax), K._p(self.omax), self.D,
-                self.n, self.S, K._p(J), J.shape[1] * J.shape[2], J.shape[2], K._stream())
+        Jint = self.Jint if Jint is None else Jint
+        omax = self.omax if omax is None else omax
+        n = Jint.shape[0]
+        assert Jint.shape[1] == g["Mpad"] and Jint.is_contiguous() and omax.shape[0] >= n and J.shape[0] >= n
+        K._call("pyglm_gram_tc_finalize", K._p(Jint), g["Mpad"], K._p(self.cmax), K._p(omax), self.D,
+                n, self.S, K._p(J), J.shape[1] * J.shape[2], J.shape[2], K._stream())
         return J
 
     def gram(self, Om, J=None):

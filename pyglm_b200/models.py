@@ -201,6 +201,13 @@ class NonlinearAutoregressiveModel(object):
 
     def _stacked_hypers(self):
         regs = self.regressions
+        src = getattr(self, "_hyper_src", None)
+        if src is not None:
+            # fast path: the hyper-parameters are still the row views resample_network() handed out
+            sigma_W, mu_W, rho, views = src
+            if all(r._S_w is v[0] and r._mu_w is v[1] and r._rho is v[2] for r, v in zip(regs, views)):
+                return dict(rho=rho, mu_w=mu_W, S_w=sigma_W, mu_b=np.array([r.mu_b[0] for r in regs]),
+                            S_b=np.array([r.S_b[0, 0] for r in regs]))
         return dict(rho=np.stack([r.rho for r in regs]), mu_w=np.stack([r.mu_w for r in regs]),
                     S_w=np.stack([r.S_w for r in regs]), mu_b=np.array([r.mu_b[0] for r in regs]),
                     S_b=np.array([r.S_b[0, 0] for r in regs]))
@@ -247,10 +254,21 @@ class HierarchicalNonlinearAutoregressiveModel(NonlinearAutoregressiveModel):
                 net.resample((self.adjacency, self.weights))
             net.set_state(comm.broadcast_object(net.get_state() if comm.rank == 0 else None))
         sigma_W, mu_W, rho = net.sigma_W, net.mu_W, net.rho
+        N, B = self.N, self.B
+        fast = (sigma_W.shape == (N, N, B, B) and mu_W.shape == (N, N, B) and rho.shape == (N, N)
+                and all(hasattr(reg, "_S_w") for reg in self.regressions))
+        views = []
         for n, reg in enumerate(self.regressions):
-            reg.S_w = sigma_W[n]
-            reg.mu_w = mu_W[n]
-            reg.rho = rho[n]
+            if fast:
+                # what the property setters do for full-shape arrays (pass through uncopied), minus 3N shape checks
+                v = (sigma_W[n], mu_W[n], rho[n])
+                reg._S_w, reg._mu_w, reg._rho = v
+                views.append(v)
+            else:
+                reg.S_w = sigma_W[n]
+                reg.mu_w = mu_W[n]
+                reg.rho = rho[n]
+        self._hyper_src = (sigma_W, mu_W, rho, views) if fast else None
 
 
 GLM = NonlinearAutoregressiveModel

@@ -260,6 +260,45 @@ def test_gram_tc_matches_oracle(K, T, N, B, n_loc, S):
         np.testing.assert_allclose(np.tril(J[j, :D, :D]), np.tril(Jr), rtol=RTOL, atol=0)
 
 
+class _MaxWith(object):
+    """Stand-in for the time-sharded communicator of ONE slab: all_reduce_max folds in the maxima the other slabs
+    would contribute (given up front), so a single GPU can play every rank in turn."""
+    world, rank = 2, 0
+
+    def __init__(self, *tensors):
+        self.pending = list(tensors)
+
+    def all_reduce_max(self, t):
+        if t.dtype == torch.float64:
+            other = self.pending.pop(0)
+            t.copy_(torch.maximum(t, other[:t.shape[0]]))
+        return t
+
+
+@pytest.mark.parametrize("T,cut,N,B,n_loc,S", [(1000, 437, 5, 2, 7, 4), (3000, 1984, 6, 3, 20, 4)])
+def test_gram_tc_time_slabs_sum_to_the_unsharded_integers(K, T, cut, N, B, n_loc, S):
+    """Time-sharded tensor-core Gram: with the scales taken over the whole recording and the
+    dither keyed by the global bin, the int64 sums of the slabs add up to the single-GPU sums bit for bit."""
+    Xp, X, om = _tc_inputs(K, T, N, B, n_loc, seed=T)
+    D = N * B + 1
+    om_d = K.to_device(om)
+    full = K.gram_tc_plan(Xp, D, n_loc, S)
+    full.slice_omega(om_d)
+    Jint_full = full.mma().clone()
+    tot = torch.zeros_like(Jint_full)
+    for lo, hi in [(0, cut), (cut, T)]:
+        comm = _MaxWith(full.cmax.clone())
+        plan = K.gram_tc_plan(Xp[lo:hi].contiguous(), D, n_loc, S, comm=comm, t_off=lo)
+        assert torch.equal(plan.cmax, full.cmax)
+        comm.pending = [full.omax.clone()]
+        plan.slice_omega(om_d[lo:hi].contiguous())
+        assert torch.equal(plan.omax, full.omax)
+        tot += plan.mma()
+    assert torch.equal(tot, Jint_full)
+    J = full.finalize(K.zeros(n_loc, full.ldx, full.ldx), Jint=tot)
+    assert torch.equal(J, full.finalize(K.zeros(n_loc, full.ldx, full.ldx)))
+
+
 def test_gram_tc_rejects_signed_design(K):
     rng = np.random.default_rng(3)
     Xp = K.pack_design(K.to_device(rng.standard_normal((200, 8))))

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _chain(comm, shard, n_sweeps=3):
+def _chain(comm, shard, n_sweeps=3, gram="auto"):
     from pyglm_b200.models import SparseBernoulliGLM
     from pyglm_b200.utils.basis import cosine_basis
     N, B, L, T = 10, 2, 20, 5000
@@ -29,7 +29,7 @@ def _chain(comm, shard, n_sweeps=3):
     Y = (np.random.default_rng(3).random((T, N)) < 0.08).astype(np.float64)
     np.random.seed(0)
     m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=77, comm=comm,
-                           shard=shard)
+                           shard=shard, gram=gram)
     m.add_data(Y, host_X=False)
     lls = []
     for _ in range(n_sweeps):
@@ -38,7 +38,7 @@ def _chain(comm, shard, n_sweeps=3):
     return m.adjacency, m.weights, m.biases, np.array(lls)
 
 
-def _worker(rank, world, port, shard, out):
+def _worker(rank, world, port, shard, out, gram="auto"):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -47,7 +47,7 @@ def _worker(rank, world, port, shard, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from pyglm_b200.distributed import Comm
-        A, W, b, lls = _chain(Comm(), shard)
+        A, W, b, lls = _chain(Comm(), shard, gram=gram)
         if rank == 0:
             np.savez(out, A=A, W=W, b=b, lls=lls)
     finally:
@@ -68,3 +68,21 @@ def test_two_gpu_chain_matches_single_gpu(tmp_path, shard):
     np.testing.assert_allclose(g["W"], W0, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(g["b"], b0, rtol=1e-8)
     np.testing.assert_allclose(g["lls"], lls0, rtol=1e-9)
+
+
+def test_two_gpu_time_sharded_tensor_core_gram(tmp_path):
+    """Time-sharded psi / PG / tcgen05 Gram with the exact int64 reduce-scatter of the integer partial sums: J is the
+    single-GPU J bit for bit (same digits, same integer sums, same draws); h = X~^T kappa is an FP64 all-reduce, so
+    the chain agrees with the 1-GPU tensor-core chain to round-off, with identical adjacency."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from pyglm_b200.distributed import Comm
+    A0, W0, b0, lls0 = _chain(Comm(), "neuron", gram="tc")
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_worker, args=(2, _free_port(), "time", out, "tc"), nprocs=2, join=True)
+    g = np.load(out)
+    assert np.array_equal(g["A"], A0)
+    np.testing.assert_allclose(g["W"], W0, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(g["b"], b0, rtol=1e-9)
+    np.testing.assert_allclose(g["lls"], lls0, rtol=1e-11)
