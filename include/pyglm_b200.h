@@ -116,6 +116,16 @@ int pyglm_spike_slab_update(int N, int B, int n_loc,
                             double* P_workspace, double* logodds, double* ml, int* status,
                             pyglm_stream_t stream);
 
+/* (6) forward simulation.  pyglm/models.py:98-151 (generate) with pyglm/regression.py:528-541 (rvs): T sequential
+ * steps x[t] = Y[t-L:t]^T flipud(basis), psi = Wm x[t] + bias, Y[t] = u < logistic(psi), as one persistent thread-block
+ * cluster.  Wm (N x N*B) = model.weights reshaped (models.py:124); Xp (T x ldx) must arrive zeroed with the bias column
+ * set (row 0 is the zero-history row); columns [0, N*B) of the other rows are written with the same fma order as
+ * pyglm_filter_spikes, so Xp equals the filter of Y bit for bit.  Y (T x N) receives 0/1; U (T x N) or NULL receives
+ * the uniforms (Philox stream (seed, call_id, t*N + n)), which lets a test replay the recursion on the host. */
+int pyglm_generate(const double* Wm, const double* bias, const double* basis, int N, int B, int L, long long T,
+                   unsigned long long seed, unsigned call_id, double* Xp, int ldx, double* Y, double* U,
+                   pyglm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

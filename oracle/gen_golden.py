@@ -200,6 +200,26 @@ def full_sweep_case():
     return out
 
 
+def generate_case():
+    """The reference's own generate() (models.py:98-151) on a network with excitatory and inhibitory weights; the
+    uniforms it consumed are numpy.random.rand(T, N) under the same seed (rvs draws N per step, regression.py:539)."""
+    N, B, L, T = 5, 2, 15, 400
+    rng = np.random.default_rng(42)
+    basis = cosine_basis(B=B, L=L) / L
+    model = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.))
+    for n, reg in enumerate(model.regressions):
+        reg.a = rng.random(N) < 0.6
+        reg.W = rng.standard_normal((N, B)) * 2.0
+        reg.W[n, :] = -2.0
+        reg.b = np.array([-1.5 + 0.2 * n])
+    np.random.seed(1234)
+    X, Y = model.generate(T=T, keep=False)
+    np.random.seed(1234)
+    U = np.random.rand(T, N)
+    return dict(basis=basis, weights=model.weights, biases=model.biases, adjacency=model.adjacency, U=U, X=X,
+                Y=np.asarray(Y, dtype=np.float64))
+
+
 def basis_table():
     out = {}
     for (B, L) in [(1, 100), (2, 100), (3, 100), (3, 10), (5, 50)]:
@@ -214,6 +234,7 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(OUT, "kat_cfg2.npz"), **kat_case(27, 3, 100, 100000, False))
     np.savez_compressed(os.path.join(OUT, "reference_tests.npz"), **reference_tests())
     np.savez_compressed(os.path.join(OUT, "full_sweep.npz"), **full_sweep_case())
+    np.savez_compressed(os.path.join(OUT, "generate.npz"), **generate_case())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
     k = np.load(os.path.join(OUT, "kat_cfg2.npz"))

@@ -205,6 +205,23 @@ def model_means(X, A, W, bias):
     return np.column_stack([mean(X, A[n], W[n], bias[n:n + 1]) for n in range(A.shape[0])])
 
 
+def generate(weights, biases, basis, T, U):
+    """models.py:98-151 with regression.py:528-541, the draw `npr.rand(N) < p` replaced by the given uniforms
+    U (T, N) so that a device simulation can be replayed step for step.  weights (N, N, B), biases (N,).
+    Returns X (T, N, B), Y (T, N)."""
+    N = weights.shape[0]
+    L, B = basis.shape
+    flipped = np.flipud(basis)                                   # models.py:117-122
+    Wm = weights.reshape((N, N * B))                             # models.py:124
+    Y = np.zeros((T + L, N))
+    X = np.zeros((T + L, N, B))
+    for t in range(L, T + L):
+        X[t] = Y[t - L:t].T.dot(flipped)                         # models.py:140
+        psi = Wm.dot(X[t].reshape((N * B,))) + biases            # models.py:143
+        Y[t] = U[t - L] < logistic(psi)                          # regression.py:538-539
+    return X[L:], Y[L:]
+
+
 def kappa(y):
     """kappa = a_func(y) - b_func(y)/2 = y - 1/2.  regression.py:510-511."""
     return y - 0.5

@@ -30,14 +30,27 @@ def time_partition(T, world, rank):
     return lo, min(T, lo + per)
 
 
+_HOST_GROUPS = {}
+
+
 class Comm(object):
-    """Thin wrapper over a torch.distributed process group (None -> single process)."""
+    """Thin wrapper over a torch.distributed process group (None -> single process).
+
+    Host objects (the network state rank 0 draws each sweep) travel over a gloo side group: an NCCL object
+    broadcast is ordered behind whatever the compute stream holds -- with pipelined sweeps that is the whole next
+    psi / PG / Gram -- and would serialise the host step with it.  Constructing a Comm is collective."""
 
     def __init__(self, group=None):
         self.enabled = dist.is_available() and dist.is_initialized()
         self.group = group
         self.world = dist.get_world_size(group) if self.enabled else 1
         self.rank = dist.get_rank(group) if self.enabled else 0
+        self.host_group = group
+        if self.enabled and self.world > 1 and dist.get_backend(group) != "gloo":
+            ranks = tuple(dist.get_process_group_ranks(group if group is not None else dist.group.WORLD))
+            if ranks not in _HOST_GROUPS:
+                _HOST_GROUPS[ranks] = dist.new_group(ranks=list(ranks), backend="gloo")
+            self.host_group = _HOST_GROUPS[ranks]
 
     def all_gather_rows(self, local):
         """local (n_max, ...) on every rank -> (world * n_max, ...), rank-major."""
@@ -84,7 +97,7 @@ class Comm(object):
         if self.world == 1:
             return obj
         box = [obj if self.rank == src else None]
-        dist.broadcast_object_list(box, src=src, group=self.group)
+        dist.broadcast_object_list(box, src=src, group=self.host_group)
         return box[0]
 
     def barrier(self):

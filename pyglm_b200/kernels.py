@@ -185,6 +185,21 @@ class CudaKernels(object):
         time-sharded runs (Xp is the slab starting at global bin t_off; scales are all-reduced over `comm`)."""
         return TcGramPlan(self, Xp, D, n_valid, S, comm=comm, t_off=t_off)
 
+    # ------------------------------------------------------------------ (6) forward simulation
+    def generate(self, Wm, bias, basis, T, seed, call_id, want_uniforms=False):
+        """Wm (N, N*B), bias (N), basis (L, B) device f64 -> (Xp (T, ldx) padded design, Y (T, N), U or None)."""
+        N, NB = Wm.shape
+        L, B = basis.shape
+        assert NB == N * B and bias.shape[0] == N and T > 0
+        ldx = pad_ldx(NB + 1)
+        Xp = self.zeros(T, ldx)
+        Xp[:, NB] = 1.0
+        Y = self.empty(T, N)
+        U = self.empty(T, N) if want_uniforms else None
+        self._call("pyglm_generate", self._p(Wm.contiguous()), self._p(bias.contiguous()), self._p(basis.contiguous()),
+                   N, B, L, T, seed, call_id, self._p(Xp), ldx, self._p(Y), self._p(U), self._stream())
+        return Xp, Y, U
+
     # ------------------------------------------------------------------ (4) spike and slab
     def scan_randomness(self, N, B, n_loc, n_off, seed, call_id):
         D = N * B + 1

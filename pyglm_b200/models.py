@@ -162,32 +162,42 @@ class NonlinearAutoregressiveModel(object):
         return self.engine.log_likelihood(dsets, A, W, b)
 
     # ------------------------------------------------------------------ simulation (models.py:98-151)
-    def generate(self, keep=True, T=100, verbose=False, intvl=10):
-        """Simulate T time bins forward from the model (sequential in time by construction).
+    def generate(self, keep=True, T=100, verbose=False, intvl=10, return_uniforms=False):
+        """Simulate T time bins forward from the model (models.py:98-151): x_t = window of the last L bins projected
+        on the flipped basis, psi_t = W x_t + b, y_t ~ Bern(logistic(psi_t)), sequential in time by construction.
 
-        Host implementation: generate() is outside the per-sweep hot path; the
-        autoregressive recursion y_t ~ Bern(logistic(W x_t + b)), x_t = window of the last L bins projected on
-        the basis, is evaluated exactly as the reference does, with the basis flipped so that row 0 is lag 1."""
+        Runs as one persistent thread-block cluster on the GPU (csrc/generate.cu).  W is `self.weights` as in the
+        reference (models.py:124 -- not masked by the adjacency).  The spikes come from the model's Philox stream,
+        not from numpy's global state, so they are statistically, not bitwise, the reference's; X equals
+        convolve_with_basis(Y) exactly.  `verbose` / `intvl` are accepted for signature compatibility (there is no
+        per-step host loop to report from).  With keep=True the simulated recording is appended to data_list and
+        its device copy is reused as is (no re-upload, no re-filtering)."""
         if T == 0:
             return np.zeros((0, self.N))
         assert isinstance(T, int), "Size must be an integer number of time bins"
         N, basis = self.N, self.basis
         L, B = basis.shape
-        flipped = np.flipud(basis)
-        assert not np.allclose(flipped, self.basis)
-        Wmat = self.weights.reshape((N, N * B))
-        b = self.biases
-        Y = np.zeros((T + L, N))
-        X = np.zeros((T + L, N, B))
-        for t in range(L, T + L):
-            if verbose and t % intvl == 0:
-                print("Generate t={}".format(t))
-            X[t] = Y[t - L:t].T.dot(flipped)
-            psi = Wmat.dot(X[t].reshape((N * B,))) + b
-            Y[t] = self.regressions[0].rvs(psi=psi)
+        assert not np.allclose(np.flipud(basis), self.basis)
+        from .engine import DeviceDataset
+        eng = self.engine
+        K = eng.K
+        self._generated = getattr(self, "_generated", 0) + 1
+        Xp, Yd, U = K.generate(K.to_device(self.weights.reshape((N, N * B))), K.to_device(self.biases),
+                               K.to_device(np.ascontiguousarray(basis, dtype=np.float64)), T, eng.seed,
+                               0x40000000 + self._generated, want_uniforms=return_uniforms)
+        Y = Yd.cpu().numpy()
+        sharded_time = eng.shard == "time" and eng.comm.world > 1
+        ds = DeviceDataset(Xp, Yd)
+        X = np.asarray(DeviceDesign(ds, N, B))
         if keep:
-            self.add_data(Y[L:], X=X[L:])
-        return X[L:], Y[L:]
+            if sharded_time:
+                self.add_data(Y, host_X=False)       # every rank simulated the same recording; keep the local slab
+            else:
+                self._dev[(id(X), id(Y))] = (X, Y, ds)
+                self.data_list.append((X, Y))
+        if return_uniforms:
+            return X, Y, U.cpu().numpy()
+        return X, Y
 
     # ------------------------------------------------------------------ rates (models.py:153-163)
     @property

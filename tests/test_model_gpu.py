@@ -221,3 +221,52 @@ def test_chain_matches_oracle_chain_readme_config():
     np.testing.assert_allclose(g_W[..., 0], c_W[..., 0], atol=0.5)
     np.testing.assert_allclose(g_W[..., 0][sure], c_W[..., 0][sure], atol=0.35)
     np.testing.assert_allclose(g_b, c_b, atol=0.12)
+
+
+@pytest.mark.parametrize("N,B,L,T", [(3, 2, 10, 500), (12, 2, 20, 3000), (70, 3, 100, 1500), (400, 2, 30, 300)])
+def test_generate_replays_the_reference_recursion(N, B, L, T):
+    """generate() on the device (csrc/generate.cu) against the oracle's restatement of models.py:98-151 driven by
+    the SAME uniforms: the spikes must be identical, X must equal the causal filter of Y (test/test_generate.py:24)
+    bit for bit, and the cluster shapes 1 / 4 / 8 CTAs plus the W-streamed-from-L2 case are all covered."""
+    from pyglm_b200.models import SparseBernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+    rng = np.random.default_rng(N)
+    basis = cosine_basis(B, L=L) / L
+    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=5)
+    for n, reg in enumerate(m.regressions):
+        reg.a = rng.random(N) < 0.5
+        reg.W = rng.standard_normal((N, B)) * (3.0 / np.sqrt(N))
+        reg.W[n] = -2.0
+        reg.b = np.array([-2.0 + 0.3 * rng.standard_normal()])
+    X, Y, U = m.generate(T=T, keep=True, return_uniforms=True)
+    assert X.shape == (T, N, B) and Y.shape == (T, N) and set(np.unique(Y)) <= {0.0, 1.0}
+    Xo, Yo = O.generate(m.weights, m.biases, basis, T, U)
+    # a draw may legitimately differ only when u sits within round-off of p; then the trajectories part: find none
+    assert np.array_equal(Y, Yo)
+    np.testing.assert_allclose(X, Xo, rtol=0, atol=1e-14)
+    # kept dataset: device copy reused; equals what add_data would have computed from Y
+    m2 = SparseBernoulliGLM(N, basis=basis, seed=5)
+    m2.add_data(Y)
+    assert np.array_equal(np.asarray(m2.data_list[0][0]), X)
+    assert m.data_list[-1][1] is Y and np.isfinite(m.log_likelihood())
+    # a second call continues with fresh randomness
+    X2, Y2 = m.generate(T=T, keep=False)
+    assert not np.array_equal(Y2, Y)
+
+
+def test_generate_rate_statistics():
+    """The simulated spikes follow the model: mean spike count vs mean of logistic(psi) over a long run."""
+    from pyglm_b200.models import SparseBernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+    N, B, L, T = 8, 2, 50, 200000
+    basis = cosine_basis(B, L=L) / L
+    np.random.seed(3)
+    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=11)
+    for n, reg in enumerate(m.regressions):
+        reg.a[n] = True
+        reg.W[n, :] = -2.0
+    X, Y = m.generate(T=T, keep=True)
+    p = m.means[0]
+    se = np.sqrt((p * (1 - p)).sum(0)) / T
+    assert np.all(np.abs(Y.mean(0) - p.mean(0)) < 5 * se)
+    assert m.generate(T=0) .shape == (0, N)

@@ -128,3 +128,13 @@ def test_full_sweep_with_injected_randomness(golden):
     np.testing.assert_allclose(W, g["W1"], rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(bias, g["b1"], rtol=1e-10)
     assert O.model_log_likelihood(X, Y, A, W, bias) == pytest.approx(float(g["ll1"]), rel=1e-11)
+
+
+def test_generate_matches_reference(golden):
+    """oracle.generate against the reference's own generate() (models.py:98-151) on the uniforms it consumed."""
+    g = golden("generate.npz")
+    X, Y = O.generate(g["weights"], g["biases"], g["basis"], g["U"].shape[0], g["U"])
+    assert np.array_equal(Y, g["Y"])
+    np.testing.assert_allclose(X, g["X"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(X.reshape(X.shape[0], -1),
+                               O.convolve_with_basis(Y, g["basis"]).reshape(X.shape[0], -1), atol=1e-14)
