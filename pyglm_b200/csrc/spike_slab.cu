@@ -53,6 +53,7 @@ struct SpikeSlabArgs {
     double* logodds;                                   // optional (n_loc, N): log-odds per scan step
     double* ml;                                        // optional (n_loc,): marginal likelihood of the final a
     int* status;                                       // (n_loc,) 0 ok, 1 = a Schur complement lost positive definiteness
+    int debug;                                         // PYGLM_SS_DEBUG=1: CTA 0 prints its cycles per phase (profiling aid)
 };
 
 template <int SS_THREADS>
@@ -783,14 +784,267 @@ struct FastCtx {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Blocked dense factorisations for the two phases of the update that are NOT inherently sequential.
+//   BUILD  P = (Jp_SS)^-1 for the active set the scan starts from.  Bordering one block at a time (as the scan must)
+//          costs two latency-bound passes over P per block; here the matrix is gathered once and inverted in place by
+//          the symmetric sweep operator, GW columns per step:  D = A_pp^-1,  T = A_op D,  A_oo -= T A_op^T (lower
+//          triangle only),  A_op = T,  A_pp = -D;  after all blocks A = -(Jp_SS)^-1.  K/GW passes instead of 2K/B.
+//   DRAW   [W_S; b] = L^-T (L^-1 hp + z) with Jp_SS = L L^T in ascending coordinate order, bias last -- literally
+//          sample_gaussian(J=, h=) (regression.py:334): right-looking blocked Cholesky in place, the forward solve of
+//          hp carried along the panel updates, one blocked back-substitution.  -sum log L_ii + 1/2 |L^-1 hp|^2 is the
+//          posterior part of _marginal_likelihood (regression.py:369-376).
+// The panels of a step live in shared memory ([b][row] layout: conflict-free for lanes that walk along a row of P);
+// the pivot block is factorised by one warp in shared memory.  Measured on cfg3 (K ~ 265): BUILD 5.3 M -> see
+// profiles/, DRAW 5.0 M cycles before.
+constexpr int GW = 8;
+
+template <int NTHR>
+struct Blocked {
+    static constexpr int NWARP = NTHR / 32;
+    double* P; int ldp;
+    double *Ft, *Tt;           // [GW][ldt]
+    double* M8;                // [GW*GW] pivot block, M8[GW*GW] = positive-definite flag
+    int ldt, tid, lane, warp;
+
+    // P[i][j] -= sum_b T[b][i] * F[b][j]   for lo <= j <= i < K, rows and columns in [s0, s1) excluded
+    __device__ __forceinline__ void tri_update(int K, int lo, int s0, int s1, const double* T, const double* F) {
+        for (int i0 = lo + warp * 2; i0 < K; i0 += NWARP * 2) {
+            const int i1 = i0 + 1;
+            const bool ok0 = !(i0 >= s0 && i0 < s1), ok1 = (i1 < K) && !(i1 >= s0 && i1 < s1);
+            if (!ok0 && !ok1) continue;
+            double t0[GW], t1[GW];
+#pragma unroll
+            for (int b = 0; b < GW; ++b) { t0[b] = T[b * ldt + i0]; t1[b] = T[b * ldt + min(i1, K - 1)]; }
+            double* row0 = P + (size_t)i0 * ldp;
+            double* row1 = P + (size_t)min(i1, K - 1) * ldp;
+            const int jend = ok1 ? i1 : i0;
+            for (int j0 = lo + lane; j0 <= jend; j0 += 128) {
+                double p0[4], p1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u;
+                    p0[u] = (ok0 && j <= i0) ? row0[j] : 0.0;
+                    p1[u] = (ok1 && j <= i1) ? row1[j] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u;
+                    if (j <= jend && !(j >= s0 && j < s1)) {
+                        double a0 = p0[u], a1 = p1[u];
+#pragma unroll
+                        for (int b = 0; b < GW; ++b) {
+                            const double f = F[b * ldt + j];
+                            a0 -= t0[b] * f;
+                            a1 -= t1[b] * f;
+                        }
+                        if (ok0 && j <= i0) row0[j] = a0;
+                        if (ok1 && j <= i1) row1[j] = a1;
+                    }
+                }
+            }
+        }
+    }
+
+    // pivot block (lower triangle of P at [k0, k0+w)) -> M8: full symmetric (sym) or lower with zero upper, identity padded
+    __device__ __forceinline__ void load_pivot(int k0, int w, bool sym) {
+        if (tid < GW * GW) {
+            const int r = tid / GW, c = tid - r * GW;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < w && c < w) v = (c <= r) ? P[(size_t)(k0 + r) * ldp + k0 + c] : (sym ? P[(size_t)(k0 + c) * ldp + k0 + r] : 0.0);
+            M8[tid] = v;
+        }
+    }
+
+    // warp 0: M8 <- M8^-1 (Gauss-Jordan, no pivoting: the block is a Schur complement of an SPD matrix)
+    __device__ __forceinline__ bool inv8(int w) {
+        bool ok = true;
+        const int e0 = lane, e1 = lane + 32;
+        const int r0 = e0 / GW, c0 = e0 - r0 * GW, r1 = e1 / GW, c1 = e1 - r1 * GW;
+        for (int k = 0; k < w; ++k) {
+            const double d = M8[k * GW + k];
+            ok = ok && (d > 0.0);
+            const double id = 1.0 / d;
+            const double ark0 = M8[r0 * GW + k], akc0 = M8[k * GW + c0], a0 = M8[e0];
+            const double ark1 = M8[r1 * GW + k], akc1 = M8[k * GW + c1], a1 = M8[e1];
+            const double n0 = (r0 == k) ? ((c0 == k) ? id : akc0 * id) : ((c0 == k) ? -ark0 * id : a0 - ark0 * akc0 * id);
+            const double n1 = (r1 == k) ? ((c1 == k) ? id : akc1 * id) : ((c1 == k) ? -ark1 * id : a1 - ark1 * akc1 * id);
+            __syncwarp();
+            M8[e0] = n0; M8[e1] = n1;
+            __syncwarp();
+        }
+        return ok;
+    }
+
+    // warp 0: lower triangle of M8 <- its Cholesky factor
+    __device__ __forceinline__ bool chol8(int w) {
+        bool ok = true;
+        const int e0 = lane, e1 = lane + 32;
+        const int r0 = e0 / GW, c0 = e0 - r0 * GW, r1 = e1 / GW, c1 = e1 - r1 * GW;
+        for (int k = 0; k < w; ++k) {
+            const double d = M8[k * GW + k];
+            ok = ok && (d > 0.0);
+            const double il = rsqrt(d);
+            const double ark0 = M8[r0 * GW + k], ack0 = M8[c0 * GW + k], a0 = M8[e0];
+            const double ark1 = M8[r1 * GW + k], ack1 = M8[c1 * GW + k], a1 = M8[e1];
+            // column k: a_ik / sqrt(d) (diagonal: sqrt(d)); trailing lower triangle: a_ij - a_ik a_jk / d
+            const double n0 = (c0 == k) ? ((r0 == k) ? d * il : ark0 * il) : a0 - ark0 * ack0 * (il * il);
+            const double n1 = (c1 == k) ? ((r1 == k) ? d * il : ark1 * il) : a1 - ark1 * ack1 * (il * il);
+            __syncwarp();
+            if (r0 >= k && c0 >= k && c0 <= r0) M8[e0] = n0;
+            if (r1 >= k && c1 >= k && c1 <= r1) M8[e1] = n1;
+            __syncwarp();
+        }
+        return ok;
+    }
+
+    // Lower triangle of P (K x K, SPD) -> full symmetric inverse, in place.  false: not positive definite.
+    __device__ __forceinline__ bool invert(int K) {
+        for (int k0 = 0; k0 < K; k0 += GW) {
+            const int w = min(GW, K - k0), k1 = k0 + w;
+            load_pivot(k0, w, true);
+            __syncthreads();
+            if (warp == 0) {
+                const bool ok = inv8(w);
+                if (lane == 0) M8[GW * GW] = ok ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            if (M8[GW * GW] == 0.0) return false;
+            for (int j = tid; j < K; j += NTHR) {
+                double f[GW];
+                const bool inp = (j >= k0 && j < k1);
+#pragma unroll
+                for (int b = 0; b < GW; ++b)
+                    f[b] = (b < w && !inp) ? ((j < k0) ? P[(size_t)(k0 + b) * ldp + j] : P[(size_t)j * ldp + k0 + b]) : 0.0;
+#pragma unroll
+                for (int b = 0; b < GW; ++b) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int c = 0; c < GW; ++c) t += f[c] * M8[c * GW + b];
+                    Ft[b * ldt + j] = f[b];
+                    Tt[b * ldt + j] = inp ? 0.0 : t;
+                }
+            }
+            __syncthreads();
+            tri_update(K, 0, k0, k1, Tt, Ft);
+            for (int j = tid; j < K; j += NTHR) {
+                if (j >= k0 && j < k1) continue;
+                for (int b = 0; b < w; ++b) {
+                    if (j < k0) P[(size_t)(k0 + b) * ldp + j] = Tt[b * ldt + j];
+                    else P[(size_t)j * ldp + k0 + b] = Tt[b * ldt + j];
+                }
+            }
+            if (tid < GW * GW) {
+                const int r = tid / GW, c = tid - r * GW;
+                if (c <= r && r < w) P[(size_t)(k0 + r) * ldp + k0 + c] = -M8[tid];
+            }
+            __syncthreads();
+        }
+        for (int i = warp; i < K; i += NWARP) {           // P = -A, mirrored into the upper triangle
+            for (int j = lane; j <= i; j += 32) {
+                const double v = -P[(size_t)i * ldp + j];
+                P[(size_t)i * ldp + j] = v;
+                P[(size_t)j * ldp + i] = v;
+            }
+        }
+        __syncthreads();
+        return true;
+    }
+
+    // Lower triangle of P (K x K, SPD) -> its Cholesky factor L in place; hv (K, shared) -> L^-1 hv; *half_logdet =
+    // sum_i log L_ii.  false: not positive definite.
+    __device__ __forceinline__ bool cholesky(int K, double* hv, double* half_logdet) {
+        double ld = 0.0;
+        for (int k0 = 0; k0 < K; k0 += GW) {
+            const int w = min(GW, K - k0), k1 = k0 + w;
+            load_pivot(k0, w, false);
+            __syncthreads();
+            if (warp == 0) {
+                const bool ok = chol8(w);
+                if (lane == 0) M8[GW * GW] = ok ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            if (M8[GW * GW] == 0.0) return false;
+            double y[GW];
+#pragma unroll
+            for (int b = 0; b < GW; ++b) {
+                double v = (b < w) ? hv[k0 + b] : 0.0;
+#pragma unroll
+                for (int c = 0; c < b; ++c) v -= M8[b * GW + c] * y[c];
+                y[b] = v / M8[b * GW + b];
+                if (b < w) ld += log(M8[b * GW + b]);
+            }
+            if (tid < GW * GW) {
+                const int r = tid / GW, c = tid - r * GW;
+                if (c <= r && r < w) P[(size_t)(k0 + r) * ldp + k0 + c] = M8[tid];
+            }
+            for (int j = k1 + tid; j < K; j += NTHR) {     // panel L[j][p] = C[j][p] L_pp^-T and the forward solve
+                double v[GW];
+#pragma unroll
+                for (int b = 0; b < GW; ++b) v[b] = (b < w) ? P[(size_t)j * ldp + k0 + b] : 0.0;
+                double hj = hv[j];
+#pragma unroll
+                for (int b = 0; b < GW; ++b) {
+                    double sacc = v[b];
+#pragma unroll
+                    for (int c = 0; c < b; ++c) sacc -= v[c] * M8[b * GW + c];
+                    v[b] = sacc / M8[b * GW + b];
+                    hj -= v[b] * y[b];
+                    Tt[b * ldt + j] = v[b];
+                    if (b < w) P[(size_t)j * ldp + k0 + b] = v[b];
+                }
+                hv[j] = hj;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < GW; ++b)
+                if (tid == b && b < w) hv[k0 + b] = y[b];
+            tri_update(K, k1, -1, -1, Tt, Tt);
+            __syncthreads();
+        }
+        *half_logdet = ld;
+        return true;
+    }
+
+    // v (K, shared) <- L^-T v with L in the lower triangle of P; s: K doubles of shared scratch.
+    __device__ __forceinline__ void backsolve(int K, double* v, double* s) {
+        for (int j = tid; j < K; j += NTHR) s[j] = 0.0;
+        __syncthreads();
+        for (int k0 = ((K - 1) / GW) * GW; k0 >= 0; k0 -= GW) {
+            const int w = min(GW, K - k0);
+            load_pivot(k0, w, false);
+            __syncthreads();
+            double o[GW];
+#pragma unroll
+            for (int b = GW - 1; b >= 0; --b) {
+                double t = (b < w) ? v[k0 + b] - s[k0 + b] : 0.0;
+#pragma unroll
+                for (int c = b + 1; c < GW; ++c) t -= M8[c * GW + b] * o[c];
+                o[b] = t / M8[b * GW + b];
+            }
+            for (int j = tid; j < k0; j += NTHR) {
+                double acc = s[j];
+                for (int b = 0; b < w; ++b) acc += P[(size_t)(k0 + b) * ldp + j] * o[b];
+                s[j] = acc;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < GW; ++b)
+                if (tid == b && b < w) v[k0 + b] = o[b];
+        }
+        __syncthreads();
+    }
+};
+
 template <int B, int NTHR>
 size_t fast_smem_bytes(int N) {
     const int D = N * B + 1, Dpad = (D + 1) & ~1;
-    return ((size_t)2 * Dpad + (size_t)2 * Dpad * B + (size_t)(NTHR / 32) * (B * B + B)) * sizeof(double) +
-           ((size_t)Dpad + N) * sizeof(int);
+    return ((size_t)2 * Dpad + (size_t)2 * Dpad * B + (size_t)(NTHR / 32) * (B * B + B) +
+            (size_t)2 * GW * Dpad + GW * GW + 2) * sizeof(double) +
+           ((size_t)Dpad + N + 2) * sizeof(int);
 }
 
-template <int B, int NTHR, int MINB>
+template <int B, int NTHR, int MINB, bool BLK>
 __global__ void __launch_bounds__(NTHR, MINB)
 spike_slab_fast_kernel(SpikeSlabArgs A) {
     extern __shared__ __align__(16) double ssm[];
@@ -812,8 +1066,15 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
     c.cb = p; p += (size_t)Dpad * B;
     c.tb = p; p += (size_t)Dpad * B;
     c.part = p; p += (size_t)(NTHR / 32) * (B * B + B);
+    Blocked<NTHR> blk;
+    blk.P = c.P; blk.ldp = c.ldp; blk.ldt = Dpad;
+    blk.Ft = p; p += (size_t)GW * Dpad;
+    blk.Tt = p; p += (size_t)GW * Dpad;
+    blk.M8 = p; p += GW * GW + 2;
+    blk.tid = threadIdx.x; blk.lane = threadIdx.x & 31; blk.warp = threadIdx.x >> 5;
     c.cidx = reinterpret_cast<int*>(p);
     c.slot = c.cidx + Dpad;
+    int* ksh = c.slot + N;                                  // block-wide scalar: size of an index list
     c.tid = threadIdx.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
     c.K = 0;
     const int tid = threadIdx.x;
@@ -839,17 +1100,60 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
     int cursor = 0, fail = 0;
     double ml = 0.0;
     SmallSolve<B> w;
-    while (phase != PH_DONE) {
+    long long clk0 = clock64(), clk_build = 0, clk_scan = 0;
+    int k_build = 0, k_scan = 0, n_eval = 0, n_flip = 0;
+    if (BLK && phase == PH_BUILD_BIAS) {
+        // BUILD, blocked: index list (bias first, then the active blocks in ascending order -- the order the bordering
+        // build produces), gather Jp_SS, invert in place, mu = P hp_S
+        if (tid == 0) {
+            int K = 0;
+            c.cidx[K++] = D - 1;
+            for (int m = 0; m < N; ++m)
+                if (a[m]) {
+                    c.slot[m] = K;
+                    for (int b = 0; b < B; ++b) c.cidx[K++] = m * B + b;
+                }
+            *ksh = K;
+        }
+        __syncthreads();
+        const int K = *ksh;
+        for (int i = c.warp; i < K; i += NTHR / 32) {
+            const int ci = c.cidx[i];
+            for (int j = c.lane; j <= i; j += 32) c.P[(size_t)i * c.ldp + j] = c.Jp(ci, c.cidx[j]);
+        }
+        for (int j = tid; j < K; j += NTHR) c.tb[j] = c.hp(c.cidx[j]);
+        __syncthreads();
+        if (!blk.invert(K)) {
+            fail = 1;
+            phase = PH_DONE;
+        } else {
+            for (int i = c.warp; i < K; i += NTHR / 32) {
+                double acc = 0.0;
+                for (int j = c.lane; j < K; j += 32) acc += c.P[(size_t)i * c.ldp + j] * c.tb[j];
+                acc = warp_sum(acc);
+                if (c.lane == 0) c.mu[i] = acc;
+            }
+            __syncthreads();
+            c.K = K;
+            phase = PH_SCAN;
+            clk_build = clock64(); k_build = K;
+        }
+    }
+    while (phase != PH_DONE && !(BLK && phase == PH_DRAW)) {
         int m = -1;
         bool is_bias = false;
         if (phase == PH_BUILD_BIAS) {
             is_bias = true;
         } else if (phase == PH_BUILD) {
             while (cursor < N && !a[cursor]) ++cursor;
-            if (cursor == N) { phase = PH_SCAN; cursor = 0; continue; }
+            if (cursor == N) { phase = PH_SCAN; cursor = 0; clk_build = clock64(); k_build = c.K; continue; }
             m = cursor++;
         } else if (phase == PH_SCAN) {
-            if (cursor == N) { __syncthreads(); phase = PH_DRAW; cursor = 0; c.K = 0; continue; }
+            if (cursor == N) {
+                __syncthreads(); clk_scan = clock64(); k_scan = c.K; phase = PH_DRAW; cursor = 0; c.K = 0;
+                if (BLK) break;
+                continue;
+            }
             m = perm[cursor];
         } else {
             while (cursor < N && !a[cursor]) ++cursor;
@@ -884,6 +1188,8 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
             if (A.logodds && tid == 0) A.logodds[(size_t)ln * N + cursor] = lo;
             do_add = (pos < 0) && v;
             do_remove = (pos >= 0) && !v;
+            n_eval += (pos < 0);
+            n_flip += (do_add || do_remove);
             ++cursor;
         } else if (draw) {
             ml += w.dpost + (is_bias ? 0.5 * log(c.J0b) - 0.5 * c.h0b * c.h0b / c.J0b : cprior[m]);
@@ -906,6 +1212,42 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
         if (phase == PH_BUILD_BIAS) phase = PH_BUILD;
         else if (draw && is_bias) phase = PH_DONE;
     }
+    if (BLK && !fail && phase == PH_DRAW) {
+        // DRAW, blocked: ascending coordinate order with the bias last (np.ix_(mask, mask), regression.py:350-353)
+        __syncthreads();
+        if (tid == 0) {
+            int K = 0;
+            for (int m = 0; m < N; ++m)
+                if (a[m])
+                    for (int b = 0; b < B; ++b) c.cidx[K++] = m * B + b;
+            c.cidx[K++] = D - 1;
+            *ksh = K;
+        }
+        __syncthreads();
+        const int K = *ksh;
+        for (int i = c.warp; i < K; i += NTHR / 32) {
+            const int ci = c.cidx[i];
+            for (int j = c.lane; j <= i; j += 32) c.P[(size_t)i * c.ldp + j] = c.Jp(ci, c.cidx[j]);
+        }
+        for (int j = tid; j < K; j += NTHR) c.mu[j] = c.hp(c.cidx[j]);
+        __syncthreads();
+        double half_logdet = 0.0;
+        if (!blk.cholesky(K, c.mu, &half_logdet)) {
+            fail = 1;
+        } else {
+            double quad = 0.0;                            // every thread, same order: |L^-1 hp|^2
+            for (int j = 0; j < K; ++j) quad += c.mu[j] * c.mu[j];
+            for (int j = tid; j < K; j += NTHR) c.xs[j] = c.mu[j] + zc[c.cidx[j]];
+            __syncthreads();
+            blk.backsolve(K, c.xs, c.tb);                 // xs = L^-T (L^-1 hp + z) = Jp^-1 hp + L^-T z
+            for (int j = tid; j < K; j += NTHR) c.mu[j] = 0.0;
+            ml = -half_logdet + 0.5 * quad + 0.5 * log(c.J0b) - 0.5 * c.h0b * c.h0b / c.J0b;
+            if (A.ml && tid == 0)
+                for (int m = 0; m < N; ++m)
+                    if (a[m]) ml += cprior[m];
+            c.K = K;
+        }
+    }
     __syncthreads();
     double* Wn = A.W + (size_t)ln * N * B;
     for (int e = tid; e < N * B; e += NTHR) Wn[e] = 0.0;
@@ -920,18 +1262,21 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
     if (tid == 0) {
         if (A.ml) A.ml[ln] = fail ? nan("") : ml;
         A.status[ln] = fail;
+        if (A.debug && ln == 0)
+            printf("spike_slab cta0: build %lld cyc (K=%d)  scan %lld cyc (K=%d, %d add-evals, %d flips)  draw %lld cyc\n",
+                   clk_build - clk0, k_build, clk_scan - clk_build, k_scan, n_eval, n_flip, clock64() - clk_scan);
     }
 }
 
-template <int B, int NTHR, int MINB>
+template <int B, int NTHR, int MINB, bool BLK>
 int launch_fast(const SpikeSlabArgs& A, cudaStream_t stream) {
     const size_t smem = fast_smem_bytes<B, NTHR>(A.N);
     if (smem > 227 * 1024) {
         pyglm_set_error("pyglm_spike_slab_update: N*B=%d too large for the shared-memory state (%zu bytes)", A.N * B, smem);
         return PYGLM_ERR_INVALID;
     }
-    PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_fast_kernel<B, NTHR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spike_slab_fast_kernel<B, NTHR, MINB><<<A.n_loc, NTHR, smem, stream>>>(A);
+    PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_fast_kernel<B, NTHR, MINB, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spike_slab_fast_kernel<B, NTHR, MINB, BLK><<<A.n_loc, NTHR, smem, stream>>>(A);
     PYGLM_LAUNCH_CHECK();
     return PYGLM_OK;
 }
@@ -939,9 +1284,9 @@ int launch_fast(const SpikeSlabArgs& A, cudaStream_t stream) {
 template <int B>
 int launch_fast_variant(const SpikeSlabArgs& A, int variant, cudaStream_t stream) {
     switch (variant) {
-        case 1: return launch_fast<B, 256, 2>(A, stream);
-        case 2: return launch_fast<B, 512, 2>(A, stream);
-        default: return launch_fast<B, 512, 1>(A, stream);
+        case 1: return launch_fast<B, 256, 2, true>(A, stream);
+        case 3: return launch_fast<B, 512, 1, false>(A, stream);     // bordering build / draw (the first version; A/B runs)
+        default: return launch_fast<B, 512, 1, true>(A, stream);
     }
 }
 
@@ -1006,6 +1351,9 @@ extern "C" int pyglm_spike_slab_update(int N, int B, int n_loc,
     A.J0w = J0w; A.h0w = h0w; A.J0b = J0b; A.h0b = h0b; A.cprior = cprior; A.logit_rho = logit_rho;
     A.perm = perm; A.us = us; A.z = z; A.ldz = ldz; A.do_scan = do_scan; A.a = a; A.W = W; A.bias = bias;
     A.P = P_workspace; A.logodds = logodds; A.ml = ml; A.status = status;
+    static int debug = -1;
+    if (debug < 0) { const char* e = getenv("PYGLM_SS_DEBUG"); debug = e ? atoi(e) : 0; }
+    A.debug = debug;
     const int Dpad = (D + 1) & ~1;
     size_t smem = ((size_t)2 * Dpad + (size_t)3 * Dpad * B + 2 * SS_BMAX * SS_BMAX + 3 * SS_BMAX + 8) * sizeof(double)
                 + ((size_t)Dpad + N) * sizeof(int);
