@@ -29,6 +29,11 @@ CONFIGS = {
     "cfg1": dict(N=4, B=1, L=100, T=10000),
     "cfg2": dict(N=27, B=3, L=100, T=100000),
     "cfg3": dict(N=200, B=2, L=100, T=100000),
+    # BASELINE.json configs[3] / [4]: 8-GPU workloads (time-sharded long recording; N=1000 neuron-sharded).  "cfg4r" is
+    # ONE rank's slab of cfg4 (T/8), runnable on a single GPU; profiles/probe_rank_share.py plays one rank of cfg5.
+    "cfg4": dict(N=100, B=3, L=100, T=10000000),
+    "cfg4r": dict(N=100, B=3, L=100, T=1250000),
+    "cfg5": dict(N=1000, B=1, L=100, T=1000000),
 }
 
 
@@ -288,7 +293,9 @@ def main():
             config=dict(workload=name, parallelism=("time-sharded psi/PG/Gram + reduce-scatter of the Gram partials (%s), neuron-sharded scan + "
                                      "all-gather of (a, W, b), x%d" % ("exact int64" if tc else "FP64", world)
                                      if eng.shard == "time" and world > 1 else "%s-sharded x%d" % (eng.shard, world)), gram=("tc" if tc else "fp64"),
-                        l2="inputs (X 333 MB, omega 205 MB, Z digit planes 32 GB) exceed the 126 MB L2", **cfg),
+                        l2="inputs (X %.0f MB, omega %.0f MB%s per rank) exceed the 126 MB L2"
+                           % (ds.Xp.numel() * 8 / 1e6, T_loc * eng.K.lib_ldn(n_loc) * 8 / 1e6,
+                              ", Z digit planes %.1f GB" % (plan.Zs.numel() / 1e9) if tc else ""), **cfg),
             e2e=dict(value=1e3 / e2e_ms, unit="sweeps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
             gpu_launches=int(launches),
             roofline=roof,

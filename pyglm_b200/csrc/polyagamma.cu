@@ -59,17 +59,116 @@ __device__ __forceinline__ double pg_mass_texpon(double z, double fz) {
     return 1.0 / (1.0 + qdivp);
 }
 
+// ---- single-precision screening -------------------------------------------------------------------------------
+// Every accept / reject decision of the sampler compares a uniform (or a cheap quantity) with a transcendental
+// expression.  Only the VALUE that is returned (X) has to be double precision; a comparison does not, unless the
+// two sides are close.  Each test is therefore evaluated in FP32 first (MUFU-based expf / logf / erfcf, error
+// < 1e-5 relative on these argument ranges) and decided there when the sides differ by more than 2e-4 relative;
+// otherwise -- and for NaN / overflow -- the FP64 expression of the oracle decides.  Decisions, the stream of
+// uniforms consumed and the returned values are exactly the oracle's; ~10 of the ~12 FP64 transcendentals per draw
+// become FP32.
+constexpr float PG_GUARD = 2e-4f;
+
+// +1: a < b for sure, 0: a > b for sure, -1: too close to call in single precision (or not finite)
+__device__ __forceinline__ int pg_less32(float a, float b, float scale) {
+    const float d = a - b;
+    if (!(fabsf(d) > PG_GUARD * scale)) return -1;
+    return d < 0.0f ? 1 : 0;
+}
+
+// -log(1 - u) in single precision with full relative accuracy at both ends of (0, 1)
+__device__ __forceinline__ float pg_expon32(double u) {
+    return (u < 0.5) ? -log1pf(-(float)u) : -__logf((float)(1.0 - u));
+}
+
+__device__ __forceinline__ float pg_a32(int n, float x, float lx) {
+    const float K = (n + 0.5f) * 3.14159265358979f;
+    if (x > 0.64f) return K * __expf(-0.5f * K * K * x);
+    return __expf(-1.5f * (0.451582705f + lx) + __logf(K) - 2.0f * (n + 0.5f) * (n + 0.5f) / x);
+}
+
+// the alternating-series test of pg1_draw in FP64 (the oracle's arithmetic): 1 accept, 0 reject
+__device__ __noinline__ int pg_series64(double X, double u) {
+    const double lx = (X <= PG_T) ? d_log(X) : 0.0;
+    double S = pg_a(0, X, lx);
+    const double Y = u * S;
+    int n = 0;
+    for (;;) {
+        ++n;
+        if (n & 1) { S -= pg_a(n, X, lx); if (Y <= S) return 1; }
+        else       { S += pg_a(n, X, lx); if (Y > S) return 0; }
+    }
+}
+
+__device__ __forceinline__ int pg_series(double X, double u) {
+    const float xf = (float)X, uf = (float)u;
+    // too close to the truncation point to know which branch of a_n the FP64 code takes, or tiny x (underflow)
+    if (fabsf(xf - 0.64f) < 1e-4f || !(xf > 1e-3f)) return pg_series64(X, u);
+    const float lx = __logf(xf);
+    const float a0 = pg_a32(0, xf, lx);
+    float S = a0;
+    const float Y = uf * a0;
+    for (int n = 1; n <= 6; ++n) {
+        const float an = pg_a32(n, xf, lx);
+        if (n & 1) {
+            S -= an;
+            const int c = pg_less32(S, Y, a0);            // Y <= S  <=>  not (S < Y)
+            if (c < 0) break;
+            if (c == 0) return 1;
+        } else {
+            S += an;
+            const int c = pg_less32(S, Y, a0);            // Y > S   <=>  S < Y
+            if (c < 0) break;
+            if (c == 1) return 0;
+        }
+    }
+    return pg_series64(X, u);
+}
+
+// u < mass_texpon(z)?  (the branch choice of pg1_draw)
+__device__ __forceinline__ bool pg_pick_texpon(double u, double z, double fz) {
+    if (z >= 12.0) return false;                              // mass taken as 0, see pg_mass_texpon
+    const float zf = (float)z, fzf = (float)fz;
+    const float b = 1.25f * (0.64f * zf - 1.0f), a = -1.25f * (0.64f * zf + 1.0f);
+    const float phib = 0.5f * erfcf(-b * 0.70710678f), phia = 0.5f * erfcf(-a * 0.70710678f);
+    const float q = 1.27323954f * fzf * (__expf(fzf * 0.64f - zf) * phib + __expf(fzf * 0.64f + zf) * phia);
+    const float m = 1.0f / (1.0f + q);
+    const int c = pg_less32((float)u, m, 1.0f);
+    if (c >= 0) return c == 1;
+    return u < pg_mass_texpon(z, fz);
+}
+
 __device__ __forceinline__ double pg_rtigauss(double z, PgRng& r) {
     const double t = PG_T;
     double X = t + 1.0;
     if (PG_T_RECIP > z) {
-        double alpha = 0.0;
-        while (r.unif() > alpha) {
-            double E1 = r.expon(), E2 = r.expon();
-            while (E1 * E1 > 2.0 * E2 / t) { E1 = r.expon(); E2 = r.expon(); }
+        bool first = true;
+        for (;;) {
+            const double ua = r.unif();
+            if (!first) {                                     // while (unif > alpha), alpha = exp(-z^2 X / 2)
+                const float al = __expf(-0.5f * (float)(z * z * X));
+                const int c = pg_less32(al, (float)ua, 1.0f); // alpha < u: continue the loop
+                const bool again = (c >= 0) ? (c == 1) : (ua > d_exp(-0.5 * z * z * X));
+                if (!again) break;
+            }
+            first = false;
+            double u1, u2;
+            for (;;) {                                        // until E1^2 <= 2 E2 / t
+                u1 = r.unif(); u2 = r.unif();
+                const float e1 = pg_expon32(u1), e2 = pg_expon32(u2);
+                const float lhs = e1 * e1, rhs = 3.125f * e2;
+                const int c = pg_less32(rhs, lhs, fmaxf(lhs, rhs));   // rhs < lhs: reject the pair
+                bool reject;
+                if (c >= 0) reject = (c == 1);
+                else {
+                    const double E1 = -d_log(1.0 - u1), E2 = -d_log(1.0 - u2);
+                    reject = E1 * E1 > 2.0 * E2 / t;
+                }
+                if (!reject) break;
+            }
+            const double E1 = -d_log(1.0 - u1);
             X = 1.0 + E1 * t;
             X = t / (X * X);
-            alpha = d_exp(-0.5 * z * z * X);
         }
     } else {
         const double mu = 1.0 / z;
@@ -86,25 +185,16 @@ __device__ __forceinline__ double pg_rtigauss(double z, PgRng& r) {
 __device__ double pg1_draw(double psi, PgRng& r) {
     const double z = fabs(psi) * 0.5;
     const double fz = 0.125 * PG_PI * PG_PI + 0.5 * z * z;
-    const double mass = pg_mass_texpon(z, fz);
     for (;;) {
         double X;
-        if (r.unif() < mass) X = PG_T + r.expon() / fz;
+        if (pg_pick_texpon(r.unif(), z, fz)) X = PG_T + r.expon() / fz;
         else X = pg_rtigauss(z, r);
-        const double lx = (X <= PG_T) ? d_log(X) : 0.0;
-        double S = pg_a(0, X, lx);
-        const double Y = r.unif() * S;
-        int n = 0;
-        for (;;) {
-            ++n;
-            if (n & 1) { S -= pg_a(n, X, lx); if (Y <= S) return 0.25 * X; }
-            else       { S += pg_a(n, X, lx); if (Y > S) break; }
-        }
+        if (pg_series(X, r.unif())) return 0.25 * X;
     }
 }
 
 // grid-stride over the T x n_valid valid entries; element id = (t_off + t) * n_total + (n_off + j)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 pg_draw_kernel(const double* __restrict__ psi, int ldpsi, long long T, int n_valid, int ld_out,
                unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
                double* __restrict__ omega) {

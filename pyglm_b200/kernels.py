@@ -50,6 +50,10 @@ class CudaKernels(object):
     def _p(t):
         return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
+    @staticmethod
+    def lib_ldn(n):
+        return pad_ldn(n)
+
     def empty(self, *shape, dtype=torch.float64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 

@@ -19,14 +19,33 @@ def prior_arrays(rho, mu_w, S_w, mu_b, S_b):
     S_w = np.asarray(S_w, dtype=np.float64)
     mu_b = np.asarray(mu_b, dtype=np.float64).reshape(-1)
     S_b = np.asarray(S_b, dtype=np.float64).reshape(-1)
-    J0w = np.linalg.inv(S_w)
-    h0w = np.einsum("nmbc,nmc->nmb", J0w, mu_w)
+    B = S_w.shape[-1]
+    if B <= 2:
+        # closed forms: numpy's batched inv / slogdet pay a LAPACK call per B x B block (40000 of them at cfg3)
+        if B == 1:
+            det = S_w[..., 0, 0]
+            J0w = 1.0 / S_w
+        else:
+            s00, s01, s10, s11 = S_w[..., 0, 0], S_w[..., 0, 1], S_w[..., 1, 0], S_w[..., 1, 1]
+            det = s00 * s11 - s01 * s10
+            J0w = np.empty_like(S_w)
+            J0w[..., 0, 0], J0w[..., 0, 1], J0w[..., 1, 0], J0w[..., 1, 1] = s11 / det, -s01 / det, -s10 / det, s00 / det
+        if np.any(~(det > 0)) or np.any(~(S_w[..., 0, 0] > 0)):
+            raise ValueError("S_w must be positive definite")
+        logdet = -np.log(det)
+        h0w = (J0w * mu_w[..., None, :]).sum(-1)
+        # h0w^T S_w h0w = mu_w^T J0w mu_w = mu_w . h0w
+        quad = (mu_w * h0w).sum(-1)
+    else:
+        J0w = np.linalg.inv(S_w)
+        h0w = np.einsum("nmbc,nmc->nmb", J0w, mu_w)
+        sign, logdet = np.linalg.slogdet(J0w)
+        if np.any(sign <= 0):
+            raise ValueError("S_w must be positive definite")
+        quad = np.einsum("nmb,nmbc,nmc->nm", h0w, S_w, h0w)
     J0b = 1.0 / S_b
     h0b = J0b * mu_b
-    sign, logdet = np.linalg.slogdet(J0w)
-    if np.any(sign <= 0):
-        raise ValueError("S_w must be positive definite")
-    cprior = 0.5 * logdet - 0.5 * np.einsum("nmb,nmbc,nmc->nm", h0w, S_w, h0w)
+    cprior = 0.5 * logdet - 0.5 * quad
     with np.errstate(divide="ignore"):
         logit_rho = np.log(rho) - np.log1p(-rho)
     do_scan = ~np.all((rho < 1e-6) | (rho > 1 - 1e-6), axis=1)
