@@ -5,8 +5,10 @@
 
 A "step" is one Gibbs sweep (psi -> PG -> weighted Gram -> spike-and-slab update of all neurons -> host network
 step) over one synthetic recording.  Default workload = BASELINE.json's metric config: N=200, B=2, L=100, T=1e5
-(configs[2], "cfg3"), which fits one B200; with --gpus N the N=200 neurons are sharded over N ranks (strong
-scaling: total work fixed), X replicated, one NCCL all-gather of (a, W, b) per sweep.
+(configs[2], "cfg3"), which fits one B200.  With --gpus N (strong scaling: total work fixed) the default is the hybrid
+partition: psi / PG / Gram over N time slabs, an exact int64 NCCL reduce-scatter of the integer Gram partials over the
+neuron axis, the scan neuron-sharded, one all-gather of the new (a, W, b) rows; --shard neuron is the pure
+neuron-sharded layout of BASELINE.json (X and the 32 GB of Z digit planes replicated: HBM-bound on Z).
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream around exactly K sweeps, barrier +
 synchronize on both sides, max over ranks.  `value` uses device-resident data and a device-only timed region of

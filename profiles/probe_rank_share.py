@@ -58,7 +58,10 @@ def main():
     a = ap.parse_args()
     cfg = CONFIGS[a.config]
     N, B, L, T = cfg["N"], cfg["B"], cfg["L"], cfg["T"]
-    Y = synthetic_spikes(T, N)
+    if T * N > 4e8:        # cfg5: 8 GB of float64 spikes -- draw them in slabs
+        Y = np.concatenate([synthetic_spikes(T // 10, N, seed=s) for s in range(10)])
+    else:
+        Y = synthetic_spikes(T, N)
     for world in [int(w) for w in a.worlds.split(",")]:
         np.random.seed(0)
         comm = FakeComm(world, 0) if world > 1 else None

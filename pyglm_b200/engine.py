@@ -129,7 +129,7 @@ class GibbsEngine(object):
         return self._ws[key]
 
     # ------------------------------------------------------------------ Gram dispatch
-    TC_MIN_WORK = 2e11          # pairs * T * neurons below which the FP64 kernel is already sub-millisecond
+    TC_MIN_WORK = 5e9           # pairs * T * neurons below which the FP64 kernel is used (cfg2 = 9e9: tc 0.49 ms vs 1.28 ms)
     TC_ACCEPT = 5e-10           # accepted max relative deviation from the FP64 kernel (stated tolerance 1e-9, 2x margin)
 
     def _time_sharded(self):
@@ -447,7 +447,8 @@ class GibbsEngine(object):
             raise FloatingPointError("spike-and-slab update lost positive definiteness for neuron(s) %s "
                                      "(ill-conditioned posterior precision)" % bad[:8].tolist())
         if pend_J is not None:
-            self._pending = ([id(ds) for ds in datasets], A_out, W_out, b_out, pend_J)
+            # private copies: the caller's regressions alias the returned arrays and may edit them in place
+            self._pending = ([id(ds) for ds in datasets], A_out.copy(), W_out.copy(), b_out.copy(), pend_J)
         return A_out, W_out, b_out
 
     def _h_for_scan(self, datasets):

@@ -270,3 +270,35 @@ def test_generate_rate_statistics():
     se = np.sqrt((p * (1 - p)).sum(0)) / T
     assert np.all(np.abs(Y.mean(0) - p.mean(0)) < 5 * se)
     assert m.generate(T=0) .shape == (0, N)
+
+
+def _chain_states(pipeline, edit_at=None, n_sweeps=5):
+    from pyglm_b200.models import SparseBernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+    N, B, L, T = 9, 2, 20, 4000
+    basis = cosine_basis(B, L=L) / L
+    Y = (np.random.default_rng(5).random((T, N)) < 0.08).astype(np.float64)
+    np.random.seed(0)
+    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=21)
+    m.add_data(Y)
+    m.engine.pipeline = pipeline
+    out = []
+    for k in range(n_sweeps):
+        if k == edit_at:                      # the user edits the state between sweeps (examples/synthetic.py:30-32)
+            m.regressions[2].a[:] = True
+            m.regressions[2].W[:] = 0.25
+            m.regressions[4].b[:] = -1.0
+        m.resample_model()
+        out.append((m.adjacency.copy(), m.weights.copy(), m.biases.copy()))
+    return out
+
+
+@pytest.mark.parametrize("edit_at", [None, 2])
+def test_pipelined_sweeps_equal_unpipelined(edit_at):
+    """The next sweep's psi / PG / Gram is enqueued behind the scan from the device copy of the new state
+    (engine.sweep).  That must be invisible: the chain equals the one that launches every phase from the host state,
+    bit for bit, also when the user rewrites a / W / b between sweeps (the pre-launched Gram is then discarded)."""
+    a = _chain_states(True, edit_at)
+    b = _chain_states(False, edit_at)
+    for (A1, W1, b1), (A2, W2, b2) in zip(a, b):
+        assert np.array_equal(A1, A2) and np.array_equal(W1, W2) and np.array_equal(b1, b2)
