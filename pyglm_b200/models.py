@@ -112,6 +112,14 @@ class NonlinearAutoregressiveModel(object):
         return out
 
     def _host_state(self):
+        """(A, W, b) stacked over the regressions.  After a sweep the regressions hold row VIEWS of the stacked arrays
+        the engine returned, so as long as nobody rebound regressions[n].a / .W / .b the stacked arrays themselves are
+        the state (in-place edits through the views included) and need not be rebuilt."""
+        src = getattr(self, "_state_src", None)
+        if src is not None:
+            A, W, b, views = src
+            if all(r._a is v[0] and r._W is v[1] and r._b is v[2] for r, v in zip(self.regressions, views)):
+                return A, W, b
         return self.adjacency, self.weights, self.biases
 
     # ------------------------------------------------------------------ data (models.py:66-80)
@@ -226,10 +234,12 @@ class NonlinearAutoregressiveModel(object):
         """All N regressions in one device sweep (they are conditionally independent given the data)."""
         A, W, b = self._host_state()
         A, W, b = self.engine.sweep(self._device_datasets(), A, W, b, self._stacked_hypers())
+        views = []
         for n, reg in enumerate(self.regressions):
-            reg._a = A[n]
-            reg._W = W[n]
-            reg._b = b[n:n + 1]
+            v = (A[n], W[n], b[n:n + 1])
+            reg._a, reg._W, reg._b = v
+            views.append(v)
+        self._state_src = (A, W, b, views)
 
     # ------------------------------------------------------------------ plotting (models.py:174-201)
     def plot(self, fig=None, axs=None, handles=None, title=None, figsize=(6, 3), W_lim=3,

@@ -111,28 +111,29 @@ class _IndependentGaussianMixin(_NetworkModel):
     @property
     def mu_W(self):
         N, B = self.N, self.B
-        mu = np.empty((N, N, B))
-        mu[:] = self._gaussian.mu
+        mu = np.repeat(np.reshape(self._gaussian.mu, (1, B)), N * N, axis=0)
         if self.is_diagonal_weight_special:
-            mu[np.arange(N), np.arange(N)] = self._self_gaussian.mu
-        return mu
+            mu[::N + 1] = self._self_gaussian.mu
+        return mu.reshape(N, N, B)
 
     @property
     def sigma_W(self):
         N, B = self.N, self.B
-        sigma = np.empty((N, N, B, B))
-        sigma[:] = self._gaussian.sigma
+        sigma = np.repeat(np.reshape(self._gaussian.sigma, (1, B * B)), N * N, axis=0)
         if self.is_diagonal_weight_special:
-            sigma[np.arange(N), np.arange(N)] = self._self_gaussian.sigma
-        return sigma
+            sigma[::N + 1] = np.reshape(self._self_gaussian.sigma, (B * B,))
+        return sigma.reshape(N, N, B, B)
 
     def resample(self, data=[]):
         super(_IndependentGaussianMixin, self).resample(data)
         A, W = data
-        eye = np.eye(self.N, dtype=bool)
         if self.is_diagonal_weight_special:
-            self._gaussian.resample(W[~eye & A])
-            self._self_gaussian.resample(W[eye & A])
+            # W[~eye & A] and W[eye & A] (networks.py:137-145), row-major order kept
+            N = self.N
+            off = A.copy()
+            off[np.arange(N), np.arange(N)] = False
+            self._gaussian.resample(W.reshape(N * N, self.B)[np.flatnonzero(off)])
+            self._self_gaussian.resample(W[np.arange(N), np.arange(N)][A.diagonal()])
         else:
             self._gaussian.resample(W[A])
 
