@@ -55,24 +55,26 @@ def peaks():
 
 
 def int8_peak():
-    """cuBLASLt int8 GEMM throughput measured on the pool's B200 (profiles/r01b_int8_peak.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01b_int8_peak.json")
+    """cuBLASLt int8 GEMM throughput measured on the pool's B200 (newest profiles/r*_int8_peak.json), or None."""
+    import glob
     try:
+        p = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_int8_peak.json")))[-1]
         with open(p) as f:
             d = json.load(f)
         return dict(tops=float(d["int8_gemm_8192_tops"]),
                     source="cuBLASLt int8 GEMM 8192^3 (torch._int_mm), best of 10, measured on B200: "
-                           "profiles/r01b_int8_peak.json (sustained: %.0f)" % d.get("int8_gemm_8192_sustained_tops", 0.0))
+                           "profiles/%s (sustained: %.0f)" % (os.path.basename(p), d.get("int8_gemm_8192_sustained_tops", 0.0)))
     except Exception:
         return None
 
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture
-    (profiles/r01b_ncu_key_metrics.json, same workload), in bytes; None when absent."""
-    p = os.path.join(ROOT, "profiles", "r01b_ncu_key_metrics.json")
+    (profiles/<round>_ncu_key_metrics.json, same workload; the newest round present), in bytes; None when absent."""
+    import glob
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     try:
+        p = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_key_metrics.json")))[-1]
         with open(p) as f:
             d = json.load(f)[kernel]
         tot = 0.0

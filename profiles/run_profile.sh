@@ -10,12 +10,12 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_1gpu.json 2> gpu
 cat gpurun_out/${TAG}_bench_1gpu.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 cat gpurun_out/${TAG}_bench_reference.json
-python profiles/profile_sweep.py --dgemm > gpurun_out/${TAG}_fp64_peak.json 2>&1
+python bench.py --config cfg2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_cfg2.json 2> gpurun_out/${TAG}_bench_cfg2.err
 python profiles/profile_sweep.py --int8 > gpurun_out/${TAG}_int8_peak.json 2>&1
 cat gpurun_out/${TAG}_int8_peak.json
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
     python profiles/profile_sweep.py --sweeps 2 > gpurun_out/${TAG}_launches.log 2>&1
-for k in gram_tc_kernel pg_draw_kernel spike_slab activation_kernel oslice_kernel; do
+for k in gram_tc_kernel pg_draw_kernel spike_slab activation_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_$k \
       python profiles/profile_sweep.py --sweeps 2 > gpurun_out/${TAG}_prof_$k.log 2>&1
   ncu -i gpurun_out/${TAG}_prof_$k.ncu-rep --page details > gpurun_out/${TAG}_ncu_$k.txt 2>&1

@@ -1074,7 +1074,7 @@ size_t fast_smem_bytes(int N) {
            ((size_t)Dpad + N + 2) * sizeof(int);
 }
 
-template <int B, int NTHR, int MINB, bool BLK, int C>
+template <int B, int NTHR, int MINB, bool BLK, int C, bool DBG>
 __global__ void __launch_bounds__(NTHR, MINB)
 spike_slab_fast_kernel(SpikeSlabArgs A) {
     extern __shared__ __align__(16) double ssm[];
@@ -1132,8 +1132,9 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
     int cursor = 0, fail = 0;
     double ml = 0.0;
     SmallSolve<B> w;
-    long long clk0 = clock64(), clk_build = 0, clk_scan = 0;
+    long long clk0 = DBG ? clock64() : 0, clk_build = 0, clk_scan = 0;
     int k_build = 0, k_scan = 0, n_eval = 0, n_flip = 0;
+    long long dbg_rm = 0, dbg_ev = 0, dbg_ca = 0, dbg_cr = 0, dbg_no = 0;
     if (BLK && phase == PH_BUILD_BIAS) {
         // BUILD, blocked: index list (bias first, then the active blocks in ascending order -- the order the bordering
         // build produces), gather Jp_SS, invert in place, mu = P hp_S
@@ -1168,7 +1169,7 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
             csync<C>();
             c.K = K;
             phase = PH_SCAN;
-            clk_build = clock64(); k_build = K;
+            if (DBG) { clk_build = clock64(); k_build = K; }
         }
     }
     while (phase != PH_DONE && !(BLK && phase == PH_DRAW)) {
@@ -1178,11 +1179,11 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
             is_bias = true;
         } else if (phase == PH_BUILD) {
             while (cursor < N && !a[cursor]) ++cursor;
-            if (cursor == N) { phase = PH_SCAN; cursor = 0; clk_build = clock64(); k_build = c.K; continue; }
+            if (cursor == N) { phase = PH_SCAN; cursor = 0; if (DBG) { clk_build = clock64(); k_build = c.K; } continue; }
             m = cursor++;
         } else if (phase == PH_SCAN) {
             if (cursor == N) {
-                csync<C>(); clk_scan = clock64(); k_scan = c.K; phase = PH_DRAW; cursor = 0; c.K = 0;
+                csync<C>(); if (DBG) { clk_scan = clock64(); k_scan = c.K; } phase = PH_DRAW; cursor = 0; c.K = 0;
                 if (BLK) break;
                 continue;
             }
@@ -1195,6 +1196,7 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
         const int pos = scan ? c.slot[m] : -1;
         const int coord0 = is_bias ? D - 1 : m * B;
         double S[B][B], r[B];
+        const long long t_a = DBG ? clock64() : 0;
         if (pos >= 0) {
             // removal: ml(with) - ml(without) read off P and mu, no pass over P, no barrier
 #pragma unroll
@@ -1211,6 +1213,8 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
             c.template eval_add<B>(coord0, S, r);
             small_factor<B, B>(w, S, r, -1.0);
         }
+        const long long t_b = DBG ? clock64() : 0;
+        if (DBG && scan) { if (pos >= 0) { dbg_rm += t_b - t_a; } else { dbg_ev += t_b - t_a; } }
         if (!(w.dpost == w.dpost)) { fail = 1; break; }
         bool do_add = true, do_remove = false;
         if (scan) {
@@ -1220,8 +1224,7 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
             if (A.logodds && tid == 0) A.logodds[(size_t)ln * N + cursor] = lo;
             do_add = (pos < 0) && v;
             do_remove = (pos >= 0) && !v;
-            n_eval += (pos < 0);
-            n_flip += (do_add || do_remove);
+            if (DBG) { n_eval += (pos < 0); n_flip += (do_add || do_remove); }
             ++cursor;
         } else if (draw) {
             ml += w.dpost + (is_bias ? 0.5 * log(c.J0b) - 0.5 * c.h0b * c.h0b / c.J0b : cprior[m]);
@@ -1241,6 +1244,7 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
             if (tid == 0) { c.slot[m] = -1; a[m] = 0; }
             c.commit_remove(w, pos);
         }
+        if (DBG && scan) { if (do_add) dbg_ca += clock64() - t_b; else if (do_remove) dbg_cr += clock64() - t_b; else dbg_no += clock64() - t_b; }
         if (phase == PH_BUILD_BIAS) phase = PH_BUILD;
         else if (draw && is_bias) phase = PH_DONE;
     }
@@ -1294,9 +1298,12 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
     if (tid == 0) {
         if (A.ml) A.ml[ln] = fail ? nan("") : ml;
         A.status[ln] = fail;
-        if (A.debug && ln == 0 && c.crank == 0)
+        if (DBG && A.debug && ln == 0 && c.crank == 0)
             printf("spike_slab cta0: build %lld cyc (K=%d)  scan %lld cyc (K=%d, %d add-evals, %d flips)  draw %lld cyc\n",
                    clk_build - clk0, k_build, clk_scan - clk_build, k_scan, n_eval, n_flip, clock64() - clk_scan);
+        if (DBG && A.debug && ln == 0 && c.crank == 0)
+            printf("   scan split: removal-evals %lld  add-evals %lld  commit-add %lld  commit-remove %lld  no-flip tail %lld\n",
+                   dbg_rm, dbg_ev, dbg_ca, dbg_cr, dbg_no);
     }
 }
 
@@ -1307,7 +1314,11 @@ int launch_fast(const SpikeSlabArgs& A, cudaStream_t stream) {
         pyglm_set_error("pyglm_spike_slab_update: N*B=%d too large for the shared-memory state (%zu bytes)", A.N * B, smem);
         return PYGLM_ERR_INVALID;
     }
-    PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_fast_kernel<B, NTHR, MINB, BLK, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (A.debug) {                                        // PYGLM_SS_DEBUG=1: the instrumented instantiation
+        PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_fast_kernel<B, NTHR, MINB, BLK, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+        PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_fast_kernel<B, NTHR, MINB, BLK, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(A.n_loc * C, 1, 1);
     cfg.blockDim = dim3(NTHR, 1, 1);
@@ -1320,7 +1331,8 @@ int launch_fast(const SpikeSlabArgs& A, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PYGLM_CUDA(cudaLaunchKernelEx(&cfg, spike_slab_fast_kernel<B, NTHR, MINB, BLK, C>, A));
+    if (A.debug) PYGLM_CUDA(cudaLaunchKernelEx(&cfg, spike_slab_fast_kernel<B, NTHR, MINB, BLK, C, true>, A));
+    else PYGLM_CUDA(cudaLaunchKernelEx(&cfg, spike_slab_fast_kernel<B, NTHR, MINB, BLK, C, false>, A));
     return PYGLM_OK;
 }
 

@@ -375,10 +375,12 @@ def test_marginal_likelihood_kat(K, golden):
 
 
 @pytest.mark.parametrize("N,B,T,n_loc,seed", [(6, 2, 400, 6, 0), (27, 3, 3000, 5, 1), (40, 1, 2000, 7, 2),
-                                              (12, 4, 1500, 3, 3)])
+                                              (12, 4, 1500, 3, 3), (90, 2, 6000, 2, 4)])
 def test_spike_slab_random_vs_oracle(K, N, B, T, n_loc, seed):
     """Random problems: full regression.resample (a-scan + W draw) vs the oracle on injected draws, with
-    neuron-specific, non-isotropic priors as the NIW network step produces them (models.py:232-236)."""
+    neuron-specific, non-isotropic priors as the NIW network step produces them (models.py:232-236).  The last case
+    (D = 181, active sets of ~90 coordinates) drives the blocked inverse / Cholesky through many pivot blocks and a
+    partial last block."""
     rng = np.random.default_rng(seed)
     Y = spikes(T, N, seed=seed, rate=0.1)
     X = O.convolve_with_basis(Y, O.cosine_basis(B, 20) / 20).reshape(T, N * B)
