@@ -262,17 +262,18 @@ class HierarchicalNonlinearAutoregressiveModel(NonlinearAutoregressiveModel):
         self.resample_network()
 
     def resample_network(self):
-        """Host step (models.py:228-236).  In multi-GPU runs rank 0 draws and broadcasts the (tiny) network
-        state so every rank pushes identical hyper-parameters.  sigma_W / mu_W / rho are built once, not once
-        per neuron as the reference's property accesses do."""
+        """Host step (models.py:228-236).  sigma_W / mu_W / rho are built once, not once per neuron as the
+        reference's property accesses do."""
         net = self.network
         comm = self.engine.comm if self._engine is not None else None
-        if comm is None or comm.world == 1:
-            net.resample((self.adjacency, self.weights))
-        else:
-            if comm.rank == 0:
-                net.resample((self.adjacency, self.weights))
-            net.set_state(comm.broadcast_object(net.get_state() if comm.rank == 0 else None))
+        if comm is not None and comm.world > 1 and not getattr(self, "_rng_synced", False):
+            # Every rank draws the (tiny) network step itself, from the SAME stream: rank 0's numpy global state is
+            # handed to all ranks once, after which identical inputs (the all-gathered A, W) give identical draws on
+            # every rank -- no per-sweep host collective on the critical path between two scans.  The chain is the
+            # one a single process with rank 0's seed would produce.
+            np.random.set_state(comm.broadcast_object(np.random.get_state() if comm.rank == 0 else None))
+            self._rng_synced = True
+        net.resample((self.adjacency, self.weights))
         sigma_W, mu_W, rho = net.sigma_W, net.mu_W, net.rho
         N, B = self.N, self.B
         fast = (sigma_W.shape == (N, N, B, B) and mu_W.shape == (N, N, B) and rho.shape == (N, N)
