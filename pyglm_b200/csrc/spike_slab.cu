@@ -55,6 +55,7 @@ struct SpikeSlabArgs {
     double* ml;                                        // optional (n_loc,): marginal likelihood of the final a
     int* status;                                       // (n_loc,) 0 ok, 1 = a Schur complement lost positive definiteness
     int debug;                                         // PYGLM_SS_DEBUG=1: CTA 0 prints its cycles per phase (profiling aid)
+    int la_G;                                          // slots of the scan's lookahead table (0 = off), set by the launcher
 };
 
 template <int SS_THREADS>
@@ -597,6 +598,16 @@ struct FastCtx {
     int *cidx, *slot;
     int K, tid, lane, warp;
     int crank;                                  // rank of this CTA in the cluster working on the neuron
+    // Lookahead table of the scan: for the next la_G INACTIVE neurons in scan order, c_j = Jp[S, j-block] and
+    // t_j = P c_j are formed together in ONE pass over P (a K x K by K x (G B) product on the FP64 tensor cores) and
+    // kept current under every flip in between by rank-B corrections (shared memory only), so the scan makes one
+    // pass over P per la_G add-evaluations instead of one per evaluation.
+    static constexpr int LA_MAX = 8;
+    static constexpr int LA_COLS = 16;          // G * B <= 16: two 8-column DMMA tiles
+    double *Cb, *Tb;                            // [la_G][la_ld]
+    double *la_part, *la_E;                     // [NWARP][B][16] partial products; [LA_MAX][2][B][B] reduced E and D
+    int* cand;                                  // [LA_MAX] presynaptic neuron per slot, -1 = free
+    int la_G, la_ld;
 
     __device__ __forceinline__ double Jp(int i, int j) const {
         const int hi = max(i, j), lo = min(i, j);
@@ -610,6 +621,238 @@ struct FastCtx {
         return v;
     }
     __device__ __forceinline__ double hp(int d) const { return hn[d] + (d < NB ? h0w[d] : h0b); }
+
+    __device__ __forceinline__ int la_find(int m) const {
+        int g = -1;
+#pragma unroll
+        for (int i = 0; i < LA_MAX; ++i) g = (i < la_G && cand[i] == m) ? i : g;
+        return g;
+    }
+
+    // A (row gr, col q) of t^T or P, B (row q, col gr) of the c vectors, as dmma884 wants them (lane = 4 gr + q)
+    __device__ __forceinline__ double la_cval(int col, int n) const {
+        const int g = n / B, bb = n - g * B;
+        return (col < K && g < la_G) ? Cb[g * la_ld + col * B + bb] : 0.0;
+    }
+
+    // Fill the table with the next la_G inactive neurons of the scan (the current one first).
+    __device__ __forceinline__ void la_refill(const int* perm, int cursor) {
+        __syncthreads();
+        if (tid == 0) {
+            int g = 0;
+            for (int i = cursor; i < N && g < la_G; ++i) {
+                const int m = perm[i];
+                if (slot[m] < 0) cand[g++] = m;
+            }
+            for (; g < LA_MAX; ++g) cand[g] = -1;
+        }
+        __syncthreads();
+        for (int e = tid; e < la_G * K * B; e += NTHR) {
+            const int g = e / (K * B), rem = e - g * K * B, c1 = rem / B, bb = rem - c1 * B;
+            const int m = cand[g];
+            Cb[g * la_ld + c1 * B + bb] = (m >= 0) ? Jp(cidx[c1], m * B + bb) : 0.0;
+        }
+        __syncthreads();
+        const int gr = lane >> 2, q = lane & 3;
+        for (int rt = warp; rt * 8 < K; rt += NWARP) {      // T = P C, one 8-row tile per warp, all K columns
+            const int row = rt * 8 + gr;
+            const double* prow = P + (size_t)min(row, K - 1) * ldp;
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            for (int k0 = 0; k0 < K; k0 += 64) {
+                double av[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int col = k0 + 4 * u + q;
+                    av[u] = (row < K && col < K) ? ldP(prow + col) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int kc = k0 + 4 * u;
+                    if (kc < K) {
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) dmma884(acc[nt][0], acc[nt][1], av[u], la_cval(kc + q, nt * 8 + gr));
+                    }
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = nt * 8 + 2 * q + h, g = n / B, bb = n - g * B;
+                    if (row < K && g < la_G) Tb[g * la_ld + row * B + bb] = acc[nt][h];
+                }
+        }
+        __syncthreads();
+    }
+
+    // S = J_jj - c_j^T t_j, r = h_j - c_j^T mu from the table; t_j is copied to tb for the commit.
+    __device__ __forceinline__ void la_eval(int g, int coord0, double (&S)[B][B], double (&r)[B]) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+#pragma unroll
+            for (int b2 = 0; b2 <= b; ++b2) S[b][b2] = Jp(coord0 + b, coord0 + b2);
+            r[b] = hp(coord0 + b);
+        }
+        const double* cg = Cb + g * la_ld;
+        const double* tg = Tb + g * la_ld;
+        double ps[B][B], pr[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            pr[b] = 0.0;
+#pragma unroll
+            for (int b2 = 0; b2 < B; ++b2) ps[b][b2] = 0.0;
+        }
+        __syncthreads();                                   // `part` and tb of the previous step are no longer read
+        for (int row = tid; row < K; row += NTHR) {
+            const double m_r = mu[row];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const double cvb = cg[row * B + b];
+                tb[row * B + b] = tg[row * B + b];
+                pr[b] += cvb * m_r;
+#pragma unroll
+                for (int b2 = 0; b2 < B; ++b2) ps[b][b2] += cvb * tg[row * B + b2];
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            pr[b] = warp_sum(pr[b]);
+#pragma unroll
+            for (int b2 = 0; b2 < B; ++b2) ps[b][b2] = warp_sum(ps[b][b2]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                part[warp * PB + B * B + b] = pr[b];
+#pragma unroll
+                for (int b2 = 0; b2 < B; ++b2) part[warp * PB + b * B + b2] = ps[b][b2];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            r[b] -= warp_sum(lane < NWARP ? part[lane * PB + B * B + b] : 0.0);
+#pragma unroll
+            for (int b2 = 0; b2 <= b; ++b2) S[b][b2] -= warp_sum(lane < NWARP ? part[lane * PB + b * B + b2] : 0.0);
+        }
+    }
+
+    // Slot g leaves the table (its neuron has been visited).
+    __device__ __forceinline__ void la_release(int g) {
+        __syncthreads();
+        if (tid == 0) cand[g] = -1;
+        __syncthreads();
+    }
+
+    // The block of slot g (coordinates coord0..) is being appended with t = tb, G = S^-1 (w.G): for every other pending
+    // candidate j,  E = t^T c_j - D,  D = Jp[new block, j-block];  t_j += t (G E),  new rows of t_j = -G E,  new rows of
+    // c_j = D.  Call before commit_add (K is still the old size).
+    __device__ __forceinline__ void la_after_add(int g, const SmallSolve<B>& w, int coord0) {
+        const int gr = lane >> 2, q = lane & 3;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        for (int kc = warp * 4; kc < K; kc += NWARP * 4) {  // t^T C, the K range split over the warps
+            const int col = kc + q;
+            const double av = (gr < B && col < K) ? tb[col * B + gr] : 0.0;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma884(acc[nt][0], acc[nt][1], av, la_cval(col, nt * 8 + gr));
+        }
+        if (gr < B) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) la_part[(warp * B + gr) * LA_COLS + nt * 8 + 2 * q + h] = acc[nt][h];
+        }
+        __syncthreads();
+        if (tid < la_G * B * B) {                          // E and D of slot g2, entry (b, b2)
+            const int g2 = tid / (B * B), rem = tid - g2 * B * B, bb = rem / B, b2 = rem - bb * B;
+            const int m2 = cand[g2];
+            double e = 0.0, d = 0.0;
+            if (m2 >= 0 && g2 != g) {
+                for (int wv = 0; wv < NWARP; ++wv) e += la_part[(wv * B + bb) * LA_COLS + g2 * B + b2];
+                d = Jp(coord0 + bb, m2 * B + b2);
+                e -= d;
+            }
+            la_E[(g2 * 2 + 0) * B * B + rem] = e;
+            la_E[(g2 * 2 + 1) * B * B + rem] = d;
+        }
+        __syncthreads();
+        for (int g2 = 0; g2 < la_G; ++g2) {
+            if (g2 == g || cand[g2] < 0) continue;
+            double GE[B][B];
+#pragma unroll
+            for (int i = 0; i < B; ++i)
+#pragma unroll
+                for (int b2 = 0; b2 < B; ++b2) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < B; ++kk) v += w.G[i][kk] * la_E[(g2 * 2 + 0) * B * B + kk * B + b2];
+                    GE[i][b2] = v;
+                }
+            double* tg = Tb + g2 * la_ld;
+            double* cg = Cb + g2 * la_ld;
+            for (int row = tid; row < K; row += NTHR) {
+#pragma unroll
+                for (int b2 = 0; b2 < B; ++b2) {
+                    double v = tg[row * B + b2];
+#pragma unroll
+                    for (int i = 0; i < B; ++i) v += tb[row * B + i] * GE[i][b2];
+                    tg[row * B + b2] = v;
+                }
+            }
+            if (tid < B * B) {
+                const int i = tid / B, b2 = tid - i * B;
+                double sel = 0.0;
+#pragma unroll
+                for (int ii = 0; ii < B; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < B; ++jj) sel = (ii == i && jj == b2) ? GE[ii][jj] : sel;
+                tg[(K + i) * B + b2] = -sel;
+                cg[(K + i) * B + b2] = la_E[(g2 * 2 + 1) * B * B + i * B + b2];
+            }
+        }
+        if (tid == 0) cand[g] = -1;
+        __syncthreads();
+    }
+
+    // The block at pos is being removed (tb = P[:, pos block], w.G = P_mm^-1): t_j -= tb (G t_j[pos block]) on the
+    // remaining rows.  Call after tb has been gathered, before anything moves.
+    __device__ __forceinline__ void la_after_remove(const SmallSolve<B>& w, int pos) {
+        for (int g2 = 0; g2 < la_G; ++g2) {
+            if (cand[g2] < 0) continue;
+            double* tg = Tb + g2 * la_ld;
+            double v[B][B];
+#pragma unroll
+            for (int i = 0; i < B; ++i)
+#pragma unroll
+                for (int b2 = 0; b2 < B; ++b2) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < B; ++kk) s += w.G[i][kk] * tg[(pos + kk) * B + b2];
+                    v[i][b2] = s;
+                }
+            for (int row = tid; row < K; row += NTHR) {
+                if (row >= pos && row < pos + B) continue;
+#pragma unroll
+                for (int b2 = 0; b2 < B; ++b2) {
+                    double x = tg[row * B + b2];
+#pragma unroll
+                    for (int i = 0; i < B; ++i) x -= tb[row * B + i] * v[i][b2];
+                    tg[row * B + b2] = x;
+                }
+            }
+        }
+    }
+
+    // the rows of the last block take the place of the removed block in every table entry
+    __device__ __forceinline__ void la_move(int pos, int last) {
+        if (tid < la_G * B * B) {
+            const int g2 = tid / (B * B), rem = tid - g2 * B * B, i = rem / B, b2 = rem - i * B;
+            if (cand[g2] >= 0) {
+                Tb[g2 * la_ld + (pos + i) * B + b2] = Tb[g2 * la_ld + (last + i) * B + b2];
+                Cb[g2 * la_ld + (pos + i) * B + b2] = Cb[g2 * la_ld + (last + i) * B + b2];
+            }
+        }
+    }
 
     // Evaluate appending coordinates [coord0, coord0+BS): t = P c goes to tb; S (lower triangle of the Schur
     // complement) and r are returned in every thread.
@@ -788,10 +1031,12 @@ struct FastCtx {
             tb[c2 * B + bb] = ldP(P + (size_t)(pos + bb) * ldp + c2);
         }
         csync<C>();
+        if (la_G > 0) la_after_remove(w, pos);
         rank_update<B>(w, -1.0, false);                   // P -= t P_mm^-1 t^T,  mu_R -= P_Rm P_mm^-1 mu_m
         csync<C>();
         const int last = K - B;
         if (pos != last) {
+            if (la_G > 0) la_move(pos, last);
             for (int e = tid; e < K * B; e += NTHR) {     // rows of the last block -> rows at pos
                 const int bb = e / K, c2 = e - bb * K;
                 P[(size_t)(pos + bb) * ldp + c2] = ldP(P + (size_t)(last + bb) * ldp + c2);
@@ -1071,7 +1316,7 @@ size_t fast_smem_bytes(int N) {
     const int D = N * B + 1, Dpad = (D + 1) & ~1;
     return ((size_t)2 * Dpad + (size_t)2 * Dpad * B + (size_t)(NTHR / 32) * (B * B + B) +
             (size_t)2 * GW * Dpad + GW * GW + 2) * sizeof(double) +
-           ((size_t)Dpad + N + 2) * sizeof(int);
+           ((size_t)Dpad + N + 2 + 8) * sizeof(int);
 }
 
 template <int B, int NTHR, int MINB, bool BLK, int C, bool DBG>
@@ -1101,11 +1346,18 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
     blk.Ft = p; p += (size_t)GW * Dpad;
     blk.Tt = p; p += (size_t)GW * Dpad;
     blk.M8 = p; p += GW * GW + 2;
+    c.la_G = A.la_G; c.la_ld = Dpad * B;
+    c.Cb = p; p += (size_t)c.la_G * c.la_ld;
+    c.Tb = p; p += (size_t)c.la_G * c.la_ld;
+    c.la_part = p; p += (size_t)(NTHR / 32) * B * 16;
+    c.la_E = p; p += 16 * B * B;
     blk.tid = threadIdx.x; blk.lane = threadIdx.x & 31; blk.warp = threadIdx.x >> 5;
     blk.crank = (int)crank_of<C>();
     c.cidx = reinterpret_cast<int*>(p);
     c.slot = c.cidx + Dpad;
     int* ksh = c.slot + N;                                  // block-wide scalar: size of an index list
+    c.cand = ksh + 2;
+    if (threadIdx.x < 8) c.cand[threadIdx.x] = -1;
     c.tid = threadIdx.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
     c.crank = (int)crank_of<C>();
     c.K = 0;
@@ -1196,6 +1448,7 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
         const int pos = scan ? c.slot[m] : -1;
         const int coord0 = is_bias ? D - 1 : m * B;
         double S[B][B], r[B];
+        int la_slot = -1;
         const long long t_a = DBG ? clock64() : 0;
         if (pos >= 0) {
             // removal: ml(with) - ml(without) read off P and mu, no pass over P, no barrier
@@ -1210,7 +1463,13 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
             c.template eval_add<1>(coord0, S, r);
             small_factor<B, 1>(w, S, r, -1.0);
         } else {
-            c.template eval_add<B>(coord0, S, r);
+            if (scan && c.la_G > 0) {
+                la_slot = c.la_find(m);
+                if (la_slot < 0) { c.la_refill(perm, cursor); la_slot = c.la_find(m); }
+                c.la_eval(la_slot, coord0, S, r);
+            } else {
+                c.template eval_add<B>(coord0, S, r);
+            }
             small_factor<B, B>(w, S, r, -1.0);
         }
         const long long t_b = DBG ? clock64() : 0;
@@ -1236,6 +1495,7 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
                 c.template commit_add<1>(w, coord0, draw);
             } else {
                 small_finish<B, B>(w, r, draw ? zc : nullptr, coord0);
+                if (la_slot >= 0) c.la_after_add(la_slot, w, coord0);
                 c.template commit_add<B>(w, coord0, draw);
             }
         } else if (do_remove) {
@@ -1243,6 +1503,8 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
             csync<C>();                              // every thread has read slot[m] before it changes
             if (tid == 0) { c.slot[m] = -1; a[m] = 0; }
             c.commit_remove(w, pos);
+        } else if (la_slot >= 0) {
+            c.la_release(la_slot);                        // evaluated and left inactive
         }
         if (DBG && scan) { if (do_add) dbg_ca += clock64() - t_b; else if (do_remove) dbg_cr += clock64() - t_b; else dbg_no += clock64() - t_b; }
         if (phase == PH_BUILD_BIAS) phase = PH_BUILD;
@@ -1309,7 +1571,21 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
 
 template <int B, int NTHR, int MINB, bool BLK, int C>
 int launch_fast(const SpikeSlabArgs& A, cudaStream_t stream) {
-    const size_t smem = fast_smem_bytes<B, NTHR>(A.N) + (size_t)(C - 1) * (NTHR / 32) * (B * B + B) * sizeof(double);
+    const int Dpad_ = (A.N * B + 2) & ~1;
+    size_t smem = fast_smem_bytes<B, NTHR>(A.N) + (size_t)(C - 1) * (NTHR / 32) * (B * B + B) * sizeof(double) +
+                  ((size_t)(NTHR / 32) * B * 16 + 16 * B * B) * sizeof(double) + 8 * sizeof(int);
+    // lookahead table of the scan: as many slots as shared memory allows (<= 8, G * B <= 16); off below two slots
+    static int la_env = -1;
+    if (la_env < 0) { const char* e = getenv("PYGLM_SS_LOOKAHEAD"); la_env = e ? atoi(e) : 8; }
+    const size_t per_slot = (size_t)2 * Dpad_ * B * sizeof(double);
+    int G = (smem < 227 * 1024) ? (int)((227 * 1024 - smem) / per_slot) : 0;
+    if (G > 16 / B) G = 16 / B;
+    if (G > 8) G = 8;
+    if (G > la_env) G = la_env;
+    if (G < 2 || C != 1) G = 0;
+    smem += (size_t)G * per_slot;
+    SpikeSlabArgs A2 = A;
+    A2.la_G = G;
     if (smem > 227 * 1024) {
         pyglm_set_error("pyglm_spike_slab_update: N*B=%d too large for the shared-memory state (%zu bytes)", A.N * B, smem);
         return PYGLM_ERR_INVALID;
@@ -1331,8 +1607,8 @@ int launch_fast(const SpikeSlabArgs& A, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (A.debug) PYGLM_CUDA(cudaLaunchKernelEx(&cfg, spike_slab_fast_kernel<B, NTHR, MINB, BLK, C, true>, A));
-    else PYGLM_CUDA(cudaLaunchKernelEx(&cfg, spike_slab_fast_kernel<B, NTHR, MINB, BLK, C, false>, A));
+    if (A.debug) PYGLM_CUDA(cudaLaunchKernelEx(&cfg, spike_slab_fast_kernel<B, NTHR, MINB, BLK, C, true>, A2));
+    else PYGLM_CUDA(cudaLaunchKernelEx(&cfg, spike_slab_fast_kernel<B, NTHR, MINB, BLK, C, false>, A2));
     return PYGLM_OK;
 }
 
