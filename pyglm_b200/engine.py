@@ -49,6 +49,35 @@ class DeviceDataset(object):
         self.buffers = {}
 
 
+class DeviceMoments(object):
+    """Running first and second moments of the Gibbs samples, kept in HBM (the reference's example
+    loops pull the (T, N) rates and the full state to the host every sweep, examples/synthetic.py:51-59).  After each
+    sweep the new state rows [a | W | b] -- already on the device for the all-gather -- and, optionally, the firing
+    rates logistic(psi) of this rank's (time, neuron) block are added to sum / sum-of-squares buffers; nothing
+    crosses PCIe until moments() is called."""
+
+    def __init__(self, rates=False):
+        self.rates = bool(rates)
+        self.n = 0
+        self.s1 = self.s2 = None            # (N, N + N*B + 1) sums of the state rows
+        self.r1, self.r2 = {}, {}           # dataset index -> (T_loc, n_psi) sums of the rates
+
+    def add_state(self, state, width):
+        x = state[:, :width]
+        if self.s1 is None:
+            self.s1, self.s2 = torch.zeros_like(x), torch.zeros_like(x)
+        self.s1 += x
+        self.s2 += x * x
+        self.n += 1
+
+    def add_rates(self, di, psi, n):
+        mu = torch.sigmoid(psi[:, :n])
+        if di not in self.r1:
+            self.r1[di], self.r2[di] = torch.zeros_like(mu), torch.zeros_like(mu)
+        self.r1[di] += mu
+        self.r2[di] += mu * mu
+
+
 class GibbsEngine(object):
     def __init__(self, N, B, kernels=None, seed=0, comm=None, shard="neuron", gram="auto", gram_digits=4):
         """gram: "fp64" = FP64 DMMA kernel (gram.cu); "tc" = tcgen05 integer-digit kernel (gram_tc.cu), checked
@@ -85,6 +114,8 @@ class GibbsEngine(object):
         # Software pipelining of consecutive sweeps (see sweep()); the pre-launched Gram of the next sweep.
         self.pipeline = True
         self._pending = None
+        # Optional on-device sample statistics (DeviceMoments); None = off.
+        self.moments = None
 
     def _mark(self, name, start=None):
         if self.profile is None:
@@ -428,11 +459,23 @@ class GibbsEngine(object):
             done.record()
         # ... while the device already starts on the next sweep's psi / PG / Gram
         pend_J = None
+        mom = self.moments
+        if mom is not None and state.shape[0] == N:
+            mom.add_state(state, N + NB + 1)
         if self.pipeline and self.inject is None and datasets and nP > 0 and state.shape[0] == N:
             Wt_next = self.build_Wt_device(state, p_lo, p_hi)
             if nS > 0 and datasets:
                 self._mark("exchange", e4)
             pend_J = self._augment(datasets, Wt_next, call_base + 64)
+            if mom is not None and mom.rates:              # psi of the NEW state is already in the buffers
+                for di, ds in enumerate(datasets):
+                    mom.add_rates(di, self._buf(ds, "psi", (ds.T, Wt_next.shape[1])), nP)
+        elif mom is not None and mom.rates and datasets and nP > 0 and state.shape[0] == N:
+            Wt_next = self.build_Wt_device(state, p_lo, p_hi)
+            for di, ds in enumerate(datasets):
+                psi = self._buf(ds, "psi", (ds.T, Wt_next.shape[1]))
+                K.activation(ds.Xp, Wt_next, D, nP, out=psi)
+                mom.add_rates(di, psi, nP)
         if done is not None:
             done.synchronize()
         host = stage.numpy()

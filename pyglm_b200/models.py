@@ -213,6 +213,36 @@ class NonlinearAutoregressiveModel(object):
         A, W, b = self._host_state()
         return [self.engine.means(ds, A, W, b) for ds in self._device_datasets()]
 
+    # ------------------------------------------------------------------ sample statistics on the device
+    def start_collecting(self, rates=False):
+        """From the next sweep on, accumulate running moments of the samples in HBM (engine.DeviceMoments): the state
+        (adjacency, weights, biases) and, with rates=True, the firing rates logistic(psi) of every data set.  The
+        reference's example loop collects the same things on the host, one (T, N) D2H copy per sweep
+        (examples/synthetic.py:51-59)."""
+        from .engine import DeviceMoments
+        self.engine.moments = DeviceMoments(rates=rates)
+
+    def stop_collecting(self):
+        self.engine.moments = None
+
+    def posterior_moments(self):
+        """dict(n, A_mean (N,N), W_mean / W_var (N,N,B), b_mean / b_var (N,), rate_mean / rate_var: per data set the
+        (T_local, n_local) block this rank computes -- all of it on a single GPU -- or None)."""
+        mom = self.engine.moments
+        assert mom is not None and mom.n > 0, "call start_collecting() and run at least one sweep first"
+        N, B, n = self.N, self.B, float(mom.n)
+        m1 = (mom.s1 / n).cpu().numpy()
+        m2 = (mom.s2 / n).cpu().numpy()
+        var = np.maximum(m2 - m1 * m1, 0.0)
+        out = dict(n=mom.n, A_mean=m1[:, :N], W_mean=m1[:, N:N + N * B].reshape(N, N, B),
+                   W_var=var[:, N:N + N * B].reshape(N, N, B), b_mean=m1[:, N + N * B], b_var=var[:, N + N * B],
+                   rate_mean=None, rate_var=None)
+        if mom.rates:
+            out["rate_mean"] = [(mom.r1[di] / n).cpu().numpy() for di in sorted(mom.r1)]
+            out["rate_var"] = [np.maximum((mom.r2[di] / n).cpu().numpy() - rm * rm, 0.0)
+                               for di, rm in zip(sorted(mom.r1), out["rate_mean"])]
+        return out
+
     # ------------------------------------------------------------------ Gibbs sampling (models.py:166-171)
     def resample_model(self):
         self.resample_regressions()

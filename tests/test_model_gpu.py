@@ -302,3 +302,37 @@ def test_pipelined_sweeps_equal_unpipelined(edit_at):
     b = _chain_states(False, edit_at)
     for (A1, W1, b1), (A2, W2, b2) in zip(a, b):
         assert np.array_equal(A1, A2) and np.array_equal(W1, W2) and np.array_equal(b1, b2)
+
+
+@pytest.mark.parametrize("pipeline", [True, False])
+def test_device_moments_match_host_collection(pipeline):
+    """running moments of the samples kept in HBM equal what the reference's example loop collects on
+    the host sweep by sweep (examples/synthetic.py:51-59: adjacency, weights, rates)."""
+    from pyglm_b200.models import SparseBernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+    N, B, L, T = 7, 2, 20, 3000
+    basis = cosine_basis(B, L=L) / L
+    Y = (np.random.default_rng(8).random((T, N)) < 0.08).astype(np.float64)
+    np.random.seed(1)
+    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=4)
+    m.add_data(Y)
+    m.engine.pipeline = pipeline
+    m.resample_model()
+    m.start_collecting(rates=True)
+    As, Ws, bs, frs = [], [], [], []
+    for _ in range(6):
+        m.resample_model()
+        As.append(m.adjacency.astype(float))
+        Ws.append(m.weights.copy())
+        bs.append(m.biases.copy())
+        frs.append(m.means[0])
+    mom = m.posterior_moments()
+    assert mom["n"] == 6
+    np.testing.assert_allclose(mom["A_mean"], np.mean(As, 0), atol=1e-15)
+    np.testing.assert_allclose(mom["W_mean"], np.mean(Ws, 0), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(mom["W_var"], np.var(Ws, 0), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(mom["b_mean"], np.mean(bs, 0), rtol=1e-12)
+    np.testing.assert_allclose(mom["rate_mean"][0], np.mean(frs, 0), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(mom["rate_var"][0], np.var(frs, 0), rtol=1e-6, atol=1e-12)
+    m.stop_collecting()
+    m.resample_model()
