@@ -121,9 +121,11 @@ int pyglm_spike_slab_update(int N, int B, int n_loc,
  * cluster.  Wm (N x N*B) = model.weights reshaped (models.py:124); Xp (T x ldx) must arrive zeroed with the bias column
  * set (row 0 is the zero-history row); columns [0, N*B) of the other rows are written with the same fma order as
  * pyglm_filter_spikes, so Xp equals the filter of Y bit for bit.  Y (T x N) receives 0/1; U (T x N) or NULL receives
- * the uniforms (Philox stream (seed, call_id, t*N + n)), which lets a test replay the recursion on the host. */
+ * the uniforms (Philox stream (seed, call_id, t*N + n)), which lets a test replay the recursion on the host.
+ * gauss_sd < 0: Bernoulli spikes as above; gauss_sd >= 0: Gaussian observations Y[t] = psi + gauss_sd * z
+ * (SparseGaussianRegression.rvs, pyglm/regression.py:406-417), U then receives the standard normals z. */
 int pyglm_generate(const double* Wm, const double* bias, const double* basis, int N, int B, int L, long long T,
-                   unsigned long long seed, unsigned call_id, double* Xp, int ldx, double* Y, double* U,
+                   unsigned long long seed, unsigned call_id, double gauss_sd, double* Xp, int ldx, double* Y, double* U,
                    pyglm_stream_t stream);
 
 #ifdef __cplusplus

@@ -220,6 +220,63 @@ def generate_case():
                 Y=np.asarray(Y, dtype=np.float64))
 
 
+def gaussian_case():
+    """SparseGaussianGLM (regression.py:380-446, models.py:274-276): the reference's own sufficient statistics,
+    log-likelihood, means, one resample() per regression with every draw recorded (permutation, categorical
+    uniforms, Gaussian normals, and the (alpha, beta) handed to sample_invgamma together with the eta it returned)."""
+    from pyglm.models import SparseGaussianGLM
+    np.random.seed(21)
+    T, N, B, L = 1500, 4, 2, 15
+    basis = cosine_basis(B=B, L=L) / L
+    true = SparseGaussianGLM(N, basis=basis, regression_kwargs=dict(S_w=4.0, mu_b=0.2, eta=0.3))
+    for n, reg in enumerate(true.regressions):
+        reg.a[:] = False
+        reg.W[:] = 0.0
+        reg.a[n] = True
+        reg.W[n, :] = 0.2
+        reg.a[(n + 1) % N] = True
+        reg.W[(n + 1) % N, :] = -0.15
+        reg.b[:] = 0.2
+    _, Y = true.generate(T=T, keep=False)
+    m = SparseGaussianGLM(N, basis=basis, regression_kwargs=dict(S_w=4.0, mu_b=0.2, rho=0.4, a_0=3.0, b_0=2.5))
+    m.add_data(Y)
+    X = m.data_list[0][0]
+    out = dict(N=N, B=B, L=L, T=T, basis=basis, Y=Y, X=X, A0=m.adjacency.copy(), W0=m.weights.copy(),
+               b0=m.biases.copy(), eta0=np.array([r.eta for r in m.regressions]), ll0=m.log_likelihood(),
+               means0=m.means[0], a_0=3.0, b_0=2.5)
+    Js, hs, perms, us, zs, alphas, betas, etas = [], [], [], [], [], [], [], []
+    for n, reg in enumerate(m.regressions):
+        J, h = reg._lkhd_sufficient_statistics([(X, Y[:, n])])
+        Js.append(J)
+        hs.append(h)
+        saved = ref_reg.sample_invgamma
+
+        def rec_invgamma(alpha, beta):
+            eta = saved(alpha, beta)
+            alphas.append(alpha)
+            betas.append(beta)
+            etas.append(eta)
+            return eta
+
+        ref_reg.sample_invgamma = rec_invgamma
+        try:
+            with Recorder() as rec:
+                reg.resample([(X, Y[:, n])])
+        finally:
+            ref_reg.sample_invgamma = saved
+        perms.append(rec.perms[0])
+        us.append(np.array(rec.us))
+        z_full = np.zeros(N * B + 1)
+        z_full[np.concatenate((np.repeat(reg.a, B), [1])).astype(bool)] = rec.zs[0]
+        zs.append(z_full)
+    r0 = m.regressions[0]
+    out.update(J=np.array(Js), h=np.array(hs), perm=np.array(perms), us=np.array(us), z=np.array(zs),
+               alpha=np.array(alphas), beta=np.array(betas), eta1=np.array(etas),
+               A1=m.adjacency.copy(), W1=m.weights.copy(), b1=m.biases.copy(), ll1=m.log_likelihood(),
+               means1=m.means[0], rho=r0.rho, mu_w=r0.mu_w, S_w=r0.S_w, mu_b=r0.mu_b, S_b=r0.S_b)
+    return out
+
+
 def basis_table():
     out = {}
     for (B, L) in [(1, 100), (2, 100), (3, 100), (3, 10), (5, 50)]:
@@ -235,6 +292,7 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(OUT, "reference_tests.npz"), **reference_tests())
     np.savez_compressed(os.path.join(OUT, "full_sweep.npz"), **full_sweep_case())
     np.savez_compressed(os.path.join(OUT, "generate.npz"), **generate_case())
+    np.savez_compressed(os.path.join(OUT, "gaussian.npz"), **gaussian_case())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
     k = np.load(os.path.join(OUT, "kat_cfg2.npz"))

@@ -222,6 +222,46 @@ def generate(weights, biases, basis, T, U):
     return X[L:], Y[L:]
 
 
+# ---------------------------------------------------------------- Gaussian observations (regression.py:380-446)
+def gaussian_omega(T, eta):
+    """regression.py:419-421: omega_t = 1 / eta for every bin."""
+    return np.ones(T) / eta
+
+
+def gaussian_kappa(y, eta):
+    """regression.py:423-424."""
+    return y / eta
+
+
+def gaussian_log_likelihood_terms(X, y, a, W, b, eta):
+    """regression.py:400-404: -1/2 log(2 pi eta) - 1/2 (y - mean)^2 / eta per bin (eta is a variance)."""
+    return -0.5 * np.log(2 * np.pi * eta) - 0.5 * (y - activation(X, a, W, b)) ** 2 / eta
+
+
+def gaussian_eta_posterior(X, y, a, W, b, a_0, b_0):
+    """(alpha, beta) handed to sample_invgamma by _resample_eta (regression.py:432-445).  As in the reference the
+    residual sum of squares enters beta without the factor 1/2."""
+    T = X.shape[0]
+    return a_0 + T / 2.0, b_0 + np.sum((y - activation(X, a, W, b)) ** 2)
+
+
+def generate_gaussian(weights, biases, etas, basis, T, Z):
+    """models.py:98-151 with SparseGaussianRegression.rvs (regression.py:406-417): y_t = psi_t + sqrt(eta) z_t.  The
+    reference draws with regressions[0] only (models.py:146), i.e. with etas[0] for every neuron; Z (T, N) are the
+    standard normals.  Returns X (T, N, B), Y (T, N)."""
+    N = weights.shape[0]
+    L, B = basis.shape
+    flipped = np.flipud(basis)
+    Wm = weights.reshape((N, N * B))
+    Y = np.zeros((T + L, N))
+    X = np.zeros((T + L, N, B))
+    for t in range(L, T + L):
+        X[t] = Y[t - L:t].T.dot(flipped)
+        psi = Wm.dot(X[t].reshape((N * B,))) + biases
+        Y[t] = psi + np.sqrt(etas[0]) * Z[t - L]
+    return X[L:], Y[L:]
+
+
 def kappa(y):
     """kappa = a_func(y) - b_func(y)/2 = y - 1/2.  regression.py:510-511."""
     return y - 0.5
@@ -344,7 +384,7 @@ def deterministic_sparsity(rho):
     return np.all((rho < 1e-6) | (rho > 1 - 1e-6))
 
 
-def resample_regression(X, y, a, W, b, hyper, omega, perm, us, z_full):
+def resample_regression(X, y, a, W, b, hyper, omega, perm, us, z_full, kap=None):
     """One regression.resample (regression.py:265-280) for ONE dataset with all randomness
     injected: omega (T,), perm (N,), us (N,), z_full (N*B+1,).  z_full is indexed by
     COORDINATE: the standard normal for active coordinate d is z_full[d] (the CUDA kernel keys
@@ -353,7 +393,7 @@ def resample_regression(X, y, a, W, b, hyper, omega, perm, us, z_full):
     N, B = W.shape
     Xf = flatten_X(X, N, B)
     J_prior, h_prior = prior_sufficient_statistics(hyper['mu_w'], hyper['S_w'], hyper['mu_b'], hyper['S_b'])
-    J_l, h_l = lkhd_sufficient_statistics(Xf, omega, kappa(y))
+    J_l, h_l = lkhd_sufficient_statistics(Xf, omega, kappa(y) if kap is None else kap)   # kap: Gaussian y / eta
     J_post = J_prior + J_l
     h_post = h_prior + h_l
     rho = hyper['rho']

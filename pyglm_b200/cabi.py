@@ -38,7 +38,8 @@ SIGNATURES = {
     "pyglm_gram_tc_mma": (c_int, [ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_ll, c_int, ptr]),
     "pyglm_gram_tc_mma_probe": (c_int, [ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_ll, ptr]),
     "pyglm_gram_tc_finalize": (c_int, [ptr, c_ll, ptr, ptr, c_int, c_int, c_int, ptr, c_ll, c_int, ptr]),
-    "pyglm_generate": (c_int, [ptr, ptr, ptr, c_int, c_int, c_int, c_ll, c_ull, c_uint, ptr, c_int, ptr, ptr, ptr]),
+    "pyglm_generate": (c_int, [ptr, ptr, ptr, c_int, c_int, c_int, c_ll, c_ull, c_uint, ctypes.c_double, ptr, c_int, ptr,
+                               ptr, ptr]),
     "pyglm_spike_slab_workspace_doubles": (size_t, [c_int, c_int, c_int]),
     "pyglm_scan_randomness": (c_int, [c_int, c_int, c_int, c_int, c_ull, c_uint, ptr, ptr, ptr, c_int, ptr]),
     "pyglm_spike_slab_update": (c_int, [c_int, c_int, c_int, ptr, c_ll, c_int, ptr, c_int, ptr, ptr, ptr, ptr,

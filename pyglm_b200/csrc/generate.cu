@@ -35,8 +35,9 @@ struct GenArgs {
     unsigned call_id;
     double* Xp; int ldx;   // (T, ldx): columns [0, N*B) written here; bias / padding columns by the caller
     double* Y;             // (T, N)
-    double* U;             // optional (T, N): the uniforms used (test hook)
+    double* U;             // optional (T, N): the uniforms (Bernoulli) or standard normals (Gaussian) used (test hook)
     int w_in_smem;
+    double gauss_sd;       // < 0: Bernoulli spikes; >= 0: Gaussian observations y = psi + gauss_sd * z (regression.py:417)
 };
 
 __global__ void __launch_bounds__(GEN_THREADS, 1)
@@ -54,11 +55,13 @@ generate_kernel(const GenArgs A) {
     double* xfull = gsm;                                   // [2][NBpad]
     double* bs = xfull + 2 * NBpad;                        // [L*B]
     double* Ws = bs + ((L * B + 1) & ~1);                  // [npc][NB] when w_in_smem
-    unsigned char* yh = reinterpret_cast<unsigned char*>(Ws + (A.w_in_smem ? (size_t)A.npc * NB : 0));   // [L][npc] ring
+    const bool gauss = A.gauss_sd >= 0.0;
+    double* yd = Ws + (A.w_in_smem ? (size_t)A.npc * NB : 0);           // Gaussian: [L][npc] ring of the last L values
+    unsigned char* yh = reinterpret_cast<unsigned char*>(yd + (gauss ? (size_t)L * A.npc : 0));   // Bernoulli: [L][npc] ring
 
     for (int i = tid; i < 2 * NBpad; i += GEN_THREADS) xfull[i] = 0.0;
     for (int i = tid; i < L * B; i += GEN_THREADS) bs[i] = A.basis[i];
-    for (int i = tid; i < L * A.npc; i += GEN_THREADS) yh[i] = 0;
+    for (int i = tid; i < L * A.npc; i += GEN_THREADS) { if (gauss) yd[i] = 0.0; else yh[i] = 0; }
     if (A.w_in_smem)
         for (int i = tid; i < nown * NB; i += GEN_THREADS) Ws[i] = A.W[(size_t)n0 * NB + i];
     cluster.sync();
@@ -76,12 +79,20 @@ generate_kernel(const GenArgs A) {
                 const double psi = acc + A.bias[n];
                 PhiloxStream r;
                 r.seed(A.seed, A.call_id, (unsigned long long)t * (unsigned long long)N + (unsigned long long)n);
-                const double u = r.unif();
-                const double p = 1.0 / (1.0 + exp(-psi));
-                const int y = u < p;
-                yh[(int)(t % L) * A.npc + nl] = (unsigned char)y;
-                A.Y[(size_t)t * N + n] = (double)y;
-                if (A.U) A.U[(size_t)t * N + n] = u;
+                if (gauss) {
+                    const double z = r.norm();
+                    const double y = psi + A.gauss_sd * z;
+                    yd[(int)(t % L) * A.npc + nl] = y;
+                    A.Y[(size_t)t * N + n] = y;
+                    if (A.U) A.U[(size_t)t * N + n] = z;
+                } else {
+                    const double u = r.unif();
+                    const double p = 1.0 / (1.0 + exp(-psi));
+                    const int y = u < p;
+                    yh[(int)(t % L) * A.npc + nl] = (unsigned char)y;
+                    A.Y[(size_t)t * N + n] = (double)y;
+                    if (A.U) A.U[(size_t)t * N + n] = u;
+                }
             }
         }
         __syncthreads();
@@ -94,9 +105,16 @@ generate_kernel(const GenArgs A) {
                 double acc = 0.0;
                 int slot = (int)(t % L);                   // slot of time t+1-l for l = 1
                 const int lmax = (int)min((long long)L, t + 1);
-                for (int l = 1; l <= lmax; ++l) {
-                    if (yh[slot * A.npc + nl]) acc = fma(bs[(l - 1) * B + b], 1.0, acc);
-                    slot = (slot == 0) ? L - 1 : slot - 1;
+                if (gauss) {
+                    for (int l = 1; l <= lmax; ++l) {
+                        acc = fma(bs[(l - 1) * B + b], yd[slot * A.npc + nl], acc);
+                        slot = (slot == 0) ? L - 1 : slot - 1;
+                    }
+                } else {
+                    for (int l = 1; l <= lmax; ++l) {
+                        if (yh[slot * A.npc + nl]) acc = fma(bs[(l - 1) * B + b], 1.0, acc);
+                        slot = (slot == 0) ? L - 1 : slot - 1;
+                    }
                 }
                 A.Xp[(size_t)(t + 1) * A.ldx + (size_t)n0 * B + j] = acc;
                 for (int c = 0; c < C; ++c) cluster.map_shared_rank(xn, c)[n0 * B + j] = acc;
@@ -111,20 +129,23 @@ generate_kernel(const GenArgs A) {
 
 // Simulate T bins.  Wm (N x N*B), bias (N), basis (L x B) device doubles; Xp (T x ldx) with ldx >= N*B+1: the kernel
 // writes columns [0, N*B) of rows 1..T-1 (row 0 is the zero-history row: the caller provides Xp zeroed with the bias
-// column set); Y (T x N) receives 0/1; U (T x N) or NULL receives the uniforms.  pyglm/models.py:98-151.
+// column set); Y (T x N) receives 0/1; U (T x N) or NULL receives the uniforms.  gauss_sd >= 0 selects Gaussian
+// observations y = psi + gauss_sd * z (SparseGaussianRegression.rvs, regression.py:406-417; U then receives z).
+// pyglm/models.py:98-151.
 extern "C" int pyglm_generate(const double* Wm, const double* bias, const double* basis, int N, int B, int L, long long T,
-                              unsigned long long seed, unsigned call_id, double* Xp, int ldx, double* Y, double* U,
-                              cudaStream_t stream) {
+                              unsigned long long seed, unsigned call_id, double gauss_sd, double* Xp, int ldx, double* Y,
+                              double* U, cudaStream_t stream) {
     PYGLM_CHECK_ARG(Wm && bias && basis && Xp && Y, "pyglm_generate: null pointer");
     PYGLM_CHECK_ARG(N > 0 && B > 0 && L > 0 && T > 0 && ldx >= N * B + 1, "pyglm_generate: bad shape");
     int C = 1;
     while (C < 8 && N >= 4 * C) C *= 2;                   // at least two neurons per CTA
     GenArgs A;
     A.W = Wm; A.bias = bias; A.basis = basis; A.N = N; A.B = B; A.L = L; A.T = T; A.seed = seed; A.call_id = call_id;
-    A.Xp = Xp; A.ldx = ldx; A.Y = Y; A.U = U;
+    A.Xp = Xp; A.ldx = ldx; A.Y = Y; A.U = U; A.gauss_sd = gauss_sd;
     A.npc = (N + C - 1) / C;
     const int NB = N * B, NBpad = (NB + 1) & ~1;
-    const size_t base = ((size_t)2 * NBpad + ((L * B + 1) & ~1)) * sizeof(double) + (size_t)L * A.npc + 16;
+    const size_t base = ((size_t)2 * NBpad + ((L * B + 1) & ~1)) * sizeof(double) + (size_t)L * A.npc + 16 +
+                        (gauss_sd >= 0.0 ? (size_t)L * A.npc * sizeof(double) : 0);
     const size_t wbytes = (size_t)A.npc * NB * sizeof(double);
     PYGLM_CHECK_ARG(base <= 200 * 1024, "pyglm_generate: N*B=%d, L=%d too large for the shared-memory state", NB, L);
     A.w_in_smem = (base + wbytes <= 220 * 1024) ? 1 : 0;

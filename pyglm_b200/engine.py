@@ -494,6 +494,104 @@ class GibbsEngine(object):
             self._pending = ([id(ds) for ds in datasets], A_out.copy(), W_out.copy(), b_out.copy(), pend_J)
         return A_out, W_out, b_out
 
+    # ------------------------------------------------------------------ Gaussian observations
+    def _gaussian_stats(self, datasets):
+        """Sweep-invariant X~^T X~ (ldx, ldx), X~^T Y (N, ldx) and the number of bins, summed over the data sets
+        (regression.py:225-262 with omega = 1/eta, kappa = y/eta factored out: both are sums over time only)."""
+        key = ("gauss", tuple(id(ds) for ds in datasets))
+        if self._ws.get("gauss_key") != key:
+            K, N, D = self.K, self.N, self.D
+            G = H = None
+            T = 0
+            for ds in datasets:
+                ones = K.zeros(ds.T, pad_ldn(1))
+                ones[:, 0] = 1.0
+                Gd = K.weighted_gram(ds.Xp, ones, D, 1)[0]
+                Yp = K.zeros(ds.T, pad_ldn(N))
+                Yp[:, :N] = ds.Y
+                Hd = K.xt_kappa(ds.Xp, Yp, D, N)
+                G = Gd if G is None else G + Gd
+                H = Hd if H is None else H + Hd
+                T += ds.T
+            self._ws["gauss_key"], self._ws["gauss_val"] = key, (G, H, T)
+        return self._ws["gauss_val"]
+
+    def residual_ss(self, datasets, A, W, b):
+        """sum_t (y_{t,n} - psi_{t,n})^2 for every neuron, over all data sets: (N,) host array."""
+        K, N, D = self.K, self.N, self.D
+        Wt = self.build_Wt(A, W, b, 0, N)
+        rss = K.zeros(N)
+        for ds in datasets:
+            psi = self._buf(ds, "psi", (ds.T, Wt.shape[1]))
+            K.activation(ds.Xp, Wt, D, N, out=psi)
+            rss += ((ds.Y - psi[:, :N]) ** 2).sum(0)
+        self.d2h_bytes += 8 * N
+        return rss.cpu().numpy()
+
+    def sweep_gaussian(self, datasets, A, W, b, hypers, eta):
+        """resample_regressions() for Gaussian observations (regression.py:426-430 without the eta draw, which is
+        the caller's host step): J_n = X~^T X~ / eta_n, h_n = X~^T y_n / eta_n from the cached sums, then the same
+        spike-and-slab kernel.  Single process or neuron-sharded.  Returns (A, W, b, rss) with rss_n the residual
+        sum of squares under the NEW coefficients (what _resample_eta needs, regression.py:432-445)."""
+        K, N, B, D, ldx = self.K, self.N, self.B, self.D, self.ldx
+        comm = self.comm
+        assert not self._time_sharded(), "Gaussian observations: use shard='neuron'"
+        s_lo, s_hi = self.scan_lo, self.scan_hi
+        nS = s_hi - s_lo
+        NB = N * B
+        self.calls += 1
+        call_base = self.calls * 64
+        self._pending = None
+        width = N + NB + 2
+        state = K.zeros(self.n_max if comm.world > 1 else nS, width)
+        if nS > 0 and datasets:
+            G, H, _ = self._gaussian_stats(datasets)
+            inv_eta = K.to_device(1.0 / np.asarray(eta, dtype=np.float64)[s_lo:s_hi])
+            J_S = G.unsqueeze(0) * inv_eta[:, None, None]
+            h_S = H[s_lo:s_hi] * inv_eta[:, None]
+            pr = prior_arrays(hypers["rho"][s_lo:s_hi], hypers["mu_w"][s_lo:s_hi], hypers["S_w"][s_lo:s_hi],
+                              hypers["mu_b"][s_lo:s_hi], hypers["S_b"][s_lo:s_hi])
+            do_scan = pr.pop("do_scan")
+            a_host = np.array(A[s_lo:s_hi], dtype=np.uint8)
+            det = ~do_scan
+            a_host[det] = np.round(hypers["rho"][s_lo:s_hi][det]).astype(np.uint8)
+            prior, a_dev, do_scan_dev = self._upload_priors(pr, a_host, do_scan)
+            if self.inject is None:
+                perm, us, z = K.scan_randomness(N, B, nS, s_lo, self.seed, call_base + 63)
+            else:
+                perm = K.to_device(np.asarray(self.inject["perm"][s_lo:s_hi], dtype=np.int32))
+                us = K.to_device(np.asarray(self.inject["us"][s_lo:s_hi], dtype=np.float64))
+                z = K.to_device(np.asarray(self.inject["z"][s_lo:s_hi], dtype=np.float64))
+            P_ws = self._wsbuf("P", (nS * D * D,))
+            W_new, b_new, _, _, status = K.spike_slab_update(N, B, J_S.contiguous(), h_S.contiguous(), prior, perm,
+                                                             us, z, do_scan_dev, a_dev, P_ws=P_ws)
+            state[:nS, :N] = a_dev
+            state[:nS, N:N + NB] = W_new.reshape(nS, NB)
+            state[:nS, N + NB] = b_new
+            state[:nS, N + NB + 1] = status
+        if comm.world > 1:
+            state = comm.all_gather_rows(state)[:N]
+        host = state.cpu().numpy()
+        self.d2h_bytes += host.nbytes
+        if host[:, N + NB + 1].any():
+            bad = np.nonzero(host[:, N + NB + 1])[0]
+            raise FloatingPointError("spike-and-slab update lost positive definiteness for neuron(s) %s" % bad[:8].tolist())
+        A_out = host[:, :N] != 0
+        W_out = host[:, N:N + NB].reshape(-1, N, B).copy()
+        b_out = host[:, N + NB].copy()
+        if self.moments is not None:
+            self.moments.add_state(state, N + NB + 1)
+        return A_out, W_out, b_out, self.residual_ss(datasets, A_out, W_out, b_out)
+
+    def activations(self, ds, A, W, b):
+        """(T, N) psi for one data set: the mean of a Gaussian regression (regression.py:429-430)."""
+        N = self.N
+        Wt = self.build_Wt(A, W, b, 0, N)
+        psi = self.K.activation(ds.Xp, Wt, self.D, N)
+        out = psi[:, :N].cpu().numpy()
+        self.d2h_bytes += out.nbytes
+        return out
+
     def _h_for_scan(self, datasets):
         """Likelihood h for the scan block, summed over datasets (and over time slabs when time-sharded)."""
         s_lo, s_hi = self.scan_lo, self.scan_hi

@@ -190,8 +190,9 @@ class CudaKernels(object):
         return TcGramPlan(self, Xp, D, n_valid, S, comm=comm, t_off=t_off)
 
     # ------------------------------------------------------------------ (6) forward simulation
-    def generate(self, Wm, bias, basis, T, seed, call_id, want_uniforms=False):
-        """Wm (N, N*B), bias (N), basis (L, B) device f64 -> (Xp (T, ldx) padded design, Y (T, N), U or None)."""
+    def generate(self, Wm, bias, basis, T, seed, call_id, want_uniforms=False, gauss_sd=-1.0):
+        """Wm (N, N*B), bias (N), basis (L, B) device f64 -> (Xp (T, ldx) padded design, Y (T, N), U or None).
+        gauss_sd >= 0: Gaussian observations with that standard deviation instead of Bernoulli spikes."""
         N, NB = Wm.shape
         L, B = basis.shape
         assert NB == N * B and bias.shape[0] == N and T > 0
@@ -201,7 +202,8 @@ class CudaKernels(object):
         Y = self.empty(T, N)
         U = self.empty(T, N) if want_uniforms else None
         self._call("pyglm_generate", self._p(Wm.contiguous()), self._p(bias.contiguous()), self._p(basis.contiguous()),
-                   N, B, L, T, seed, call_id, self._p(Xp), ldx, self._p(Y), self._p(U), self._stream())
+                   N, B, L, T, seed, call_id, ctypes.c_double(gauss_sd), self._p(Xp), ldx, self._p(Y), self._p(U),
+                   self._stream())
         return Xp, Y, U
 
     # ------------------------------------------------------------------ (4) spike and slab

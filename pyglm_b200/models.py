@@ -111,6 +111,14 @@ class NonlinearAutoregressiveModel(object):
             del self._dev[key]
         return out
 
+    @property
+    def _gaussian(self):
+        """True when the regressions have Gaussian observations (regression.py:380-456)."""
+        return isinstance(self.regressions[0], _regression.SparseGaussianRegression)
+
+    def _etas(self):
+        return np.array([float(r.eta) for r in self.regressions])
+
     def _host_state(self):
         """(A, W, b) stacked over the regressions.  After a sweep the regressions hold row VIEWS of the stacked arrays
         the engine returned, so as long as nobody rebound regressions[n].a / .W / .b the stacked arrays themselves are
@@ -167,6 +175,12 @@ class NonlinearAutoregressiveModel(object):
                     dsets.append(self._device_dataset(X, Y))
                 else:
                     dsets.append(self.engine.make_dataset(data, basis=self.basis))
+        if self._gaussian:
+            # sum over bins of -1/2 log(2 pi eta) - 1/2 (y - psi)^2 / eta (regression.py:400-404)
+            eta = self._etas()
+            T = sum(ds.T for ds in dsets)
+            rss = self.engine.residual_ss(dsets, A, W, b)
+            return float(np.sum(-0.5 * T * np.log(2 * np.pi * eta) - 0.5 * rss / eta))
         return self.engine.log_likelihood(dsets, A, W, b)
 
     # ------------------------------------------------------------------ simulation (models.py:98-151)
@@ -192,7 +206,9 @@ class NonlinearAutoregressiveModel(object):
         self._generated = getattr(self, "_generated", 0) + 1
         Xp, Yd, U = K.generate(K.to_device(self.weights.reshape((N, N * B))), K.to_device(self.biases),
                                K.to_device(np.ascontiguousarray(basis, dtype=np.float64)), T, eng.seed,
-                               0x40000000 + self._generated, want_uniforms=return_uniforms)
+                               0x40000000 + self._generated, want_uniforms=return_uniforms,
+                               # Gaussian observations: regressions[0].rvs draws for every neuron (models.py:146)
+                               gauss_sd=float(np.sqrt(self.regressions[0].eta)) if self._gaussian else -1.0)
         Y = Yd.cpu().numpy()
         sharded_time = eng.shard == "time" and eng.comm.world > 1
         ds = DeviceDataset(Xp, Yd)
@@ -211,6 +227,8 @@ class NonlinearAutoregressiveModel(object):
     @property
     def means(self):
         A, W, b = self._host_state()
+        if self._gaussian:
+            return [self.engine.activations(ds, A, W, b) for ds in self._device_datasets()]
         return [self.engine.means(ds, A, W, b) for ds in self._device_datasets()]
 
     # ------------------------------------------------------------------ sample statistics on the device
@@ -263,7 +281,15 @@ class NonlinearAutoregressiveModel(object):
     def resample_regressions(self):
         """All N regressions in one device sweep (they are conditionally independent given the data)."""
         A, W, b = self._host_state()
-        A, W, b = self.engine.sweep(self._device_datasets(), A, W, b, self._stacked_hypers())
+        if self._gaussian:
+            dsets = self._device_datasets()
+            A, W, b, rss = self.engine.sweep_gaussian(dsets, A, W, b, self._stacked_hypers(), self._etas())
+            # eta_n ~ InvGamma(a_0 + T/2, b_0 + RSS_n): the host step of regression.py:432-445
+            T = sum(ds.T for ds in dsets)
+            for n, reg in enumerate(self.regressions):
+                reg.eta = float(_regression.sample_invgamma(reg.a_0 + T / 2.0, reg.b_0 + rss[n]))
+        else:
+            A, W, b = self.engine.sweep(self._device_datasets(), A, W, b, self._stacked_hypers())
         views = []
         for n, reg in enumerate(self.regressions):
             v = (A[n], W[n], b[n:n + 1])
@@ -340,6 +366,16 @@ class _DefaultMixin(object):
             regression_kwargs = dict() if regression_kwargs is None else regression_kwargs
             regressions = [self._regression_class(N, B, **regression_kwargs) for _ in range(N)]
         super(_DefaultMixin, self).__init__(N, network, regressions, B=B, basis=basis, **kwargs)
+
+
+class GaussianGLM(_DefaultMixin, NetworkGLM):
+    _network_class = _networks.NIWDenseNetwork
+    _regression_class = _regression.GaussianRegression
+
+
+class SparseGaussianGLM(_DefaultMixin, NetworkGLM):
+    _network_class = _networks.NIWSparseNetwork
+    _regression_class = _regression.SparseGaussianRegression
 
 
 class BernoulliGLM(_DefaultMixin, NetworkGLM):

@@ -214,6 +214,72 @@ def Xp_ld(D):
     return pad_ldx(D)
 
 
+def sample_invgamma(alpha, beta):
+    """pybasicbayes.util.stats.sample_invgamma as called at regression.py:398, 445: 1 / Gamma(alpha, scale = 1/beta)."""
+    return 1.0 / npr.gamma(alpha, 1.0 / np.asarray(beta, dtype=np.float64))
+
+
+class SparseGaussianRegression(_SparseScalarRegressionBase):
+    """Sparse regression with Gaussian observations of variance eta (regression.py:380-446).  The Gibbs update is
+    the Bernoulli one with omega = 1/eta and kappa = y/eta, so the sufficient statistics are X~^T X~ / eta and
+    X~^T y / eta: the same Gram and spike-and-slab kernels, no augmentation."""
+
+    def __init__(self, N, B, a_0=2.0, b_0=2.0, eta=None, **kwargs):
+        super(SparseGaussianRegression, self).__init__(N, B, **kwargs)
+        assert np.isscalar(a_0) and a_0 > 0
+        assert np.isscalar(b_0) and a_0 > 0                  # sic (regression.py:392)
+        self.a_0, self.b_0 = a_0, b_0
+        if eta is not None:
+            assert np.isscalar(eta) and eta > 0
+            self.eta = eta
+        else:
+            self.eta = float(sample_invgamma(self.a_0, self.b_0))
+
+    def log_likelihood(self, x):
+        X, y = self.extract_data(x)
+        return -0.5 * np.log(2 * np.pi * self.eta) - 0.5 * (y - self.mean(X)) ** 2 / self.eta
+
+    def rvs(self, size=[], X=None, psi=None):
+        if psi is None:
+            if X is None:
+                assert isinstance(size, int)
+                X = npr.randn(size, self.N * self.B)
+            psi = self.mean(self._flatten_X(X))
+        return psi + np.sqrt(self.eta) * npr.randn(*psi.shape)
+
+    def omega_device(self, K, Xp, y):
+        return np.ones(Xp.shape[0]) / self.eta
+
+    def omega(self, X, y):
+        return 1. / self.eta * np.ones(X.shape[0])
+
+    def kappa(self, X, y):
+        return y / self.eta
+
+    def mean(self, X):
+        return self.activation(X)
+
+    def resample(self, datas):
+        super(SparseGaussianRegression, self).resample(datas)
+        self._resample_eta(datas)
+
+    def _resample_eta(self, datas):
+        alpha, beta = self.a_0, self.b_0
+        for data in datas:
+            X, y = self.extract_data(data)
+            alpha += X.shape[0] / 2.0
+            beta += np.sum((y - self.mean(X)) ** 2)          # no factor 1/2, as regression.py:443
+        self.eta = float(sample_invgamma(alpha, beta))
+
+
+class GaussianRegression(SparseGaussianRegression):
+    """Dense weights: rho = 1 (regression.py:448-456)."""
+
+    def __init__(self, N, B, **kwargs):
+        kwargs["rho"] = np.ones(N)
+        super(GaussianRegression, self).__init__(N, B, **kwargs)
+
+
 class _SparsePGRegressionBase(_SparseScalarRegressionBase):
     """Count observations through Polya-gamma augmentation (regression.py:459-511)."""
 

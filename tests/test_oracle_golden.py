@@ -138,3 +138,35 @@ def test_generate_matches_reference(golden):
     np.testing.assert_allclose(X, g["X"], rtol=0, atol=1e-15)
     np.testing.assert_allclose(X.reshape(X.shape[0], -1),
                                O.convolve_with_basis(Y, g["basis"]).reshape(X.shape[0], -1), atol=1e-14)
+
+
+def test_gaussian_regression_matches_reference(golden):
+    """SparseGaussianGLM (regression.py:380-446): sufficient statistics, log-likelihood, means, the reference's own
+    resample() on recorded draws, and the (alpha, beta) it hands to sample_invgamma."""
+    g = golden("gaussian.npz")
+    N, B, T = int(g["N"]), int(g["B"]), int(g["T"])
+    X, Y = g["X"].reshape(T, -1), g["Y"]
+    hyper = dict(rho=g["rho"], mu_w=g["mu_w"], S_w=g["S_w"], mu_b=g["mu_b"], S_b=g["S_b"])
+    ll0 = ll1 = 0.0
+    for n in range(N):
+        eta = g["eta0"][n]
+        J, h = O.lkhd_sufficient_statistics(X, O.gaussian_omega(T, eta), O.gaussian_kappa(Y[:, n], eta))
+        np.testing.assert_allclose(J, g["J"][n], rtol=1e-12)
+        np.testing.assert_allclose(h, g["h"][n], rtol=1e-12)
+        ll0 += O.gaussian_log_likelihood_terms(X, Y[:, n], g["A0"][n], g["W0"][n], g["b0"][n:n + 1], eta).sum()
+        np.testing.assert_allclose(O.activation(X, g["A0"][n], g["W0"][n], g["b0"][n:n + 1]), g["means0"][:, n],
+                                   rtol=1e-12, atol=1e-14)
+        a, W, b = O.resample_regression(X, Y[:, n], g["A0"][n], g["W0"][n], g["b0"][n:n + 1], hyper,
+                                        O.gaussian_omega(T, eta), g["perm"][n], g["us"][n], g["z"][n],
+                                        kap=O.gaussian_kappa(Y[:, n], eta))
+        assert np.array_equal(a, g["A1"][n])
+        np.testing.assert_allclose(W, g["W1"][n], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(b[0], g["b1"][n], rtol=1e-9)
+        alpha, beta = O.gaussian_eta_posterior(X, Y[:, n], g["A1"][n], g["W1"][n], g["b1"][n:n + 1],
+                                               float(g["a_0"]), float(g["b_0"]))
+        assert alpha == g["alpha"][n]
+        np.testing.assert_allclose(beta, g["beta"][n], rtol=1e-12)
+        ll1 += O.gaussian_log_likelihood_terms(X, Y[:, n], g["A1"][n], g["W1"][n], g["b1"][n:n + 1],
+                                               g["eta1"][n]).sum()
+    np.testing.assert_allclose(ll0, float(g["ll0"]), rtol=1e-12)
+    np.testing.assert_allclose(ll1, float(g["ll1"]), rtol=1e-12)
