@@ -128,31 +128,57 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, cfg, name):
     """The reference's CPU path (numpy/OpenBLAS + OpenMP Devroye PG) as restated by the oracle port, timed on the
-    host cores.  Each step is a BOUNDED SAMPLE of the sweep: `sample_neurons` of the N postsynaptic regressions
-    (each does the full T-length psi / PG / dgemm Gram / 2N-Cholesky a-scan of regression.py:265-280), scaled to
-    a whole sweep by N / sample_neurons -- the regressions are independent and identically sized."""
+    host cores with every thread they offer.  Each step is a BOUNDED SAMPLE of the sweep, sized so that the whole
+    --steps K --warmup W run ends within a few minutes (REF_BUDGET_S): `sample_neurons` of the N postsynaptic
+    regressions (independent and identically sized: scaled by N / sample_neurons), and -- only when a full-length
+    regression does not fit the per-step budget -- the first T_s of the T time bins, with the T-proportional phases
+    (psi, PG draws, dgemm Gram; exactly linear in T) scaled by T / T_s and the 2N-Cholesky a-scan + W draw of
+    regression.py:282-340 measured in full."""
     from oracle import pyglm_oracle as O
     N, B, L, T = cfg["N"], cfg["B"], cfg["L"], cfg["T"]
     cores = os.cpu_count() or 1
     basis = O.cosine_basis(B, L) / L
     Y = synthetic_spikes(T, N)
     X = O.convolve_with_basis(Y, basis)
-    m = O.OracleSparseBernoulliGLM(N, basis, S_w=10.0, mu_b=-2.0, seed=0, pg_threads=cores)
-    m.add_data(Y, X=X)
-    sample = min(N, args.ref_neurons)
-    neurons = list(range(sample))
-    for _ in range(args.warmup if args.warmup is not None else 1):
-        m.resample_model(neurons=neurons[:1])
     steps = args.steps if args.steps is not None else 2
+    warmup = args.warmup if args.warmup is not None else 1
+    budget = float(os.environ.get("REF_BUDGET_S", "150")) / max(1, steps + warmup)
+
+    def model_on(Ts):
+        m = O.OracleSparseBernoulliGLM(N, basis, S_w=10.0, mu_b=-2.0, seed=0, pg_threads=cores)
+        m.add_data(Y[:Ts], X=X[:Ts])
+        return m
+
+    # calibration on a short prefix: cost of the T-proportional part per bin, and of the scan
+    T_cal = min(T, 10000)
+    cal = model_on(T_cal)
+    cal.resample_model(neurons=[0])
+    aug_per_bin, scan_s = cal.t_aug / T_cal, cal.t_scan
+    sample = min(N, args.ref_neurons)
+    if sample * (aug_per_bin * T + scan_s) <= budget:
+        T_s = T
+    else:
+        sample = 1
+        T_s = int(min(T, max(T_cal, (budget - scan_s) / aug_per_bin)))
+    m = model_on(T_s)
+    neurons = list(range(sample))
+    for _ in range(warmup):
+        m.resample_model(neurons=neurons[:1])
+    m.t_aug = m.t_scan = 0.0
     t0 = time.perf_counter()
     for _ in range(steps):
         m.resample_model(neurons=neurons)
-    dt = (time.perf_counter() - t0) / steps
-    sweep_s = dt * N / sample
+    wall = time.perf_counter() - t0
+    per_reg = (m.t_aug * (T / float(T_s)) + m.t_scan + max(0.0, wall - m.t_aug - m.t_scan)) / (steps * sample)
+    sweep_s = per_reg * N
     val = 1.0 / sweep_s
-    desc = "%d of %d regressions per step at full T=%d, scaled by N/%d" % (sample, N, T, sample)
+    if T_s == T:
+        desc = "%d of %d regressions per step at full T=%d, scaled by N/%d" % (sample, N, T, sample)
+    else:
+        desc = ("%d of %d regressions per step on the first %d of T=%d bins: psi / PG / dgemm Gram scaled by T/T_s, "
+                "a-scan and W draw measured in full; scaled by N/%d" % (sample, N, T_s, T, sample))
     line = dict(metric="gibbs_sweeps_per_sec", value=val, unit="sweeps/s", n_gpus=0, steps=steps,
-                warmup=args.warmup if args.warmup is not None else 1, ms_per_step=sweep_s * 1e3,
+                warmup=warmup, ms_per_step=sweep_s * 1e3,
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                 impl="reference", config=dict(workload=name, **cfg),
                 cpu_baseline=dict(value=val, unit="sweeps/s", cores=cores, kind="port", sample=desc),

@@ -479,6 +479,10 @@ class OracleSparseBernoulliGLM(object):
         self.niw = dict(mu_0=np.zeros(B), sigma_0=np.eye(B), kappa_0=1.0, nu_0=3.0)
         self.net_rho = 0.5 * np.ones((N, N))
         self.data_list = []
+        # wall-clock seconds spent in the T-proportional part (psi, PG, Gram) and in the rest (priors, a-scan, W draw)
+        # of resample_regression: lets the timed CPU baseline extrapolate from a time sub-sample (bench.py)
+        self.t_aug = 0.0
+        self.t_scan = 0.0
 
     def add_data(self, Y, X=None):
         if X is None:
@@ -490,11 +494,14 @@ class OracleSparseBernoulliGLM(object):
 
     def resample_regression(self, n):
         """regression.py:265-280 for postsynaptic neuron n."""
+        import time as _time
         N, B = self.N, self.B
         h = self.hyper[n]
+        _t0 = _time.perf_counter()
         J_prior, h_prior = prior_sufficient_statistics(h['mu_w'], h['S_w'], h['mu_b'], h['S_b'])
         J_l = np.zeros_like(J_prior)
         h_l = np.zeros_like(h_prior)
+        _t1 = _time.perf_counter()
         for X, Y in self.data_list:
             Xf = flatten_X(X, N, B)
             y = Y[:, n]
@@ -504,6 +511,7 @@ class OracleSparseBernoulliGLM(object):
             Jd, hd = lkhd_sufficient_statistics(Xf, omega, kappa(y))
             J_l += Jd
             h_l += hd
+        _t2 = _time.perf_counter()
         J_post = J_prior + J_l
         h_post = h_prior + h_l
         if deterministic_sparsity(h['rho']):
@@ -516,6 +524,8 @@ class OracleSparseBernoulliGLM(object):
         z = self.rng.standard_normal(int(m.sum()))
         Wn, bn = resample_W(J_post, h_post, a, B, z)
         self.A[n], self.W[n], self.bias[n] = a, Wn, bn[0]
+        self.t_aug += _t2 - _t1
+        self.t_scan += (_t1 - _t0) + (_time.perf_counter() - _t2)
 
     def resample_network(self):
         """models.py:228-236 + networks.py:132-149 (NIWSparseNetwork, diagonal special)."""
