@@ -13,6 +13,8 @@ namespace {
 constexpr int FILT_NX = 32;   // neurons per CTA (one per lane: coalesced S reads)
 constexpr int FILT_NY = 8;    // time rows per CTA pass
 constexpr int FILT_TT = 128;  // output time bins per CTA
+constexpr int FILT_RB = 4;    // consecutive time bins per thread (register block)
+constexpr int FILT_BB = 4;    // basis functions handled by the register-blocked path
 
 __global__ void __launch_bounds__(FILT_NX * FILT_NY)
 filter_kernel(const double* __restrict__ S, const double* __restrict__ basis, int T, int N, int L, int B,
@@ -32,6 +34,48 @@ filter_kernel(const double* __restrict__ S, const double* __restrict__ basis, in
     __syncthreads();
     if (n >= N) return;
 
+    // Register blocking: a thread produces FILT_RB consecutive time bins of its neuron for up to FILT_BB basis functions
+    // at once.  Going from lag l to l+1 the window of a bin is the previous bin's, so one new spike value and B
+    // (warp-broadcast) basis values are loaded per 4*B FMAs -- the first version loaded two operands per FMA and ran
+    // at the shared-memory bandwidth.  Every output still accumulates its taps in the order l = 1..L.
+    if (B <= FILT_BB) {
+        for (int r = ty * FILT_RB; r < FILT_TT; r += FILT_NY * FILT_RB) {
+            if (t0 + r >= T) break;
+            double acc[FILT_RB][FILT_BB];
+#pragma unroll
+            for (int k = 0; k < FILT_RB; ++k)
+#pragma unroll
+                for (int b = 0; b < FILT_BB; ++b) acc[k][b] = 0.0;
+            const double* win = Ss + (size_t)(r + L) * FILT_NX + tx;      // win[(k - l) * NX] = S[t0 + r + k - l, n]
+            double w[FILT_RB];                                             // w[k] = S[t0 + r + k - l, n], lag l = 1
+#pragma unroll
+            for (int k = 0; k < FILT_RB; ++k) w[k] = win[(k - 1) * FILT_NX];
+#pragma unroll 4
+            for (int l = 1; l <= L; ++l) {
+#pragma unroll
+                for (int b = 0; b < FILT_BB; ++b) {
+                    if (b < B) {
+                        const double bv = bs[(l - 1) * B + b];
+#pragma unroll
+                        for (int k = 0; k < FILT_RB; ++k) acc[k][b] = fma(bv, w[k], acc[k][b]);
+                    }
+                }
+#pragma unroll
+                for (int k = FILT_RB - 1; k >= 1; --k) w[k] = w[k - 1];   // lag l+1: bin k sees what bin k-1 saw
+                if (l < L) w[0] = win[-(l + 1) * FILT_NX];
+            }
+#pragma unroll
+            for (int k = 0; k < FILT_RB; ++k) {
+                const int t = t0 + r + k;
+                if (t < T) {
+#pragma unroll
+                    for (int b = 0; b < FILT_BB; ++b)
+                        if (b < B) Xp[(size_t)t * ldx + (size_t)n * B + b] = clip ? fmax(acc[k][b], 0.0) : acc[k][b];
+                }
+            }
+        }
+        return;
+    }
     for (int r = ty; r < FILT_TT; r += FILT_NY) {
         int t = t0 + r;
         if (t >= T) break;
