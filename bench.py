@@ -74,9 +74,13 @@ def ncu_traffic(kernel):
     import glob
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     try:
-        p = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_key_metrics.json")))[-1]
-        with open(p) as f:
-            d = json.load(f)[kernel]
+        d = None
+        for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_key_metrics.json")), reverse=True):
+            with open(p) as f:
+                allk = json.load(f)
+            if kernel in allk:
+                d = allk[kernel]
+                break
         tot = 0.0
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             v, u = d[k].split()
