@@ -419,8 +419,13 @@ class GibbsEngine(object):
         # new state rows [a (N) | W (N*B) | b | status], one row per neuron of the scan block (padded to n_max)
         width = N + NB + 2
         state = K.zeros(self.n_max if comm.world > 1 else nS, width)
-        if nS > 0 and datasets:
-            h_S = self._h_for_scan(datasets)
+        if nS > 0:
+            if datasets:
+                h_S = self._h_for_scan(datasets)
+            else:
+                # no data: the posterior is the prior (regression.py:237, datas = [] leaves J_lkhd = h_lkhd = 0)
+                J_S = self._wsbuf("J_nodata", (nS, ldx, ldx), zero=True)
+                h_S = self._wsbuf("h_nodata", (nS, ldx), zero=True)
             pr = prior_arrays(hypers["rho"][s_lo:s_hi], hypers["mu_w"][s_lo:s_hi], hypers["S_w"][s_lo:s_hi],
                               hypers["mu_b"][s_lo:s_hi], hypers["S_b"][s_lo:s_hi])
             do_scan = pr.pop("do_scan")

@@ -336,3 +336,22 @@ def test_device_moments_match_host_collection(pipeline):
     np.testing.assert_allclose(mom["rate_var"][0], np.var(frs, 0), rtol=1e-6, atol=1e-12)
     m.stop_collecting()
     m.resample_model()
+
+
+def test_resample_without_data_samples_the_prior():
+    """regression.py:237: with datas = [] the likelihood statistics vanish and resample() draws (a, W, b) from the prior."""
+    from pyglm_b200.models import SparseBernoulliGLM
+    np.random.seed(2)
+    N, B = 30, 2
+    m = SparseBernoulliGLM(N, B=B, regression_kwargs=dict(rho=0.3, S_w=4.0, mu_b=-1.0, S_b=0.25), seed=8,
+                           network_kwargs=dict(rho=0.3))
+    As, bs, Ws = [], [], []
+    for _ in range(40):
+        m.resample_regressions()
+        As.append(m.adjacency.mean())
+        bs.append(m.biases.copy())
+        Ws.append(m.weights[m.adjacency].ravel())
+    assert abs(np.mean(As) - 0.3) < 0.02
+    b_all, W_all = np.concatenate(bs), np.concatenate(Ws)
+    assert abs(b_all.mean() + 1.0) < 0.06 and abs(b_all.std() - 0.5) < 0.05
+    assert abs(W_all.mean()) < 0.1 and abs(W_all.std() - 2.0) < 0.1
