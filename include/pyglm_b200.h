@@ -56,6 +56,14 @@ int pyglm_means(const double* Xp, int ldx, const double* Wt, int ldw, int T, int
 int pyglm_pg_draw(const double* psi, int ldpsi, long long T, int n_valid, double* omega, int ld_out,
                   unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
                   pyglm_stream_t stream);
+/* The same draws (element by element) through the branch-compacted two-pass kernels: pass 1 takes the proposal
+ * choice for every element and finishes the exponential-tail draws, pass 2 finishes the inverse-Gaussian draws from a
+ * compacted index list so that all lanes of a warp run the same sampler.  workspace: pyglm_pg_draw_ws_bytes(T, n_valid)
+ * bytes of device memory, contents irrelevant.  Falls back to pyglm_pg_draw when T * n_valid >= 2^32 - 1. */
+size_t pyglm_pg_draw_ws_bytes(long long T, int n_valid);
+int pyglm_pg_draw_ws(const double* psi, int ldpsi, long long T, int n_valid, double* omega, int ld_out,
+                     unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
+                     void* workspace, size_t workspace_bytes, pyglm_stream_t stream);
 int pyglm_philox_uniforms(unsigned long long seed, unsigned call_id, unsigned long long elem0, int n_elem,
                           int count, double* out, pyglm_stream_t stream); /* test hook */
 

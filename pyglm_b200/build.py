@@ -30,17 +30,41 @@ def _stale():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
+def _compile(nvcc, src, obj):
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-ccbin", "/usr/bin/g++", "-c", src, "-o", obj]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return src, proc.returncode, proc.stdout
+
+
 def build_library(force=False, verbose=False):
+    """One object per .cu file (compiled in parallel, only when stale), then one link."""
     if not force and not _stale():
         return LIBPATH
-    os.makedirs(LIBDIR, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++", "-o", LIBPATH] + sources()
+    headers = glob.glob(os.path.join(CSRC, "*.cuh"))
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        newest = max(os.path.getmtime(p) for p in [src] + headers)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
+            jobs.append((src, obj))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        results = list(pool.map(lambda j: _compile(nvcc, *j), jobs))
+    for src, rc, out in results:
+        if verbose or rc != 0:
+            sys.stdout.write(out)
+        if rc != 0:
+            raise RuntimeError("nvcc failed compiling %s (exit %d)" % (os.path.basename(src), rc))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", LIBPATH] + objs
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:
         sys.stdout.write(proc.stdout)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libpyglm_b200.so (exit %d)" % proc.returncode)
+        raise RuntimeError("nvcc failed linking libpyglm_b200.so (exit %d)" % proc.returncode)
     return LIBPATH
 
 

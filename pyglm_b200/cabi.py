@@ -24,6 +24,9 @@ SIGNATURES = {
     "pyglm_loglik": (c_int, [ptr, c_int, ptr, c_int, c_int, c_int, c_int, ptr, c_int, c_int, ptr, ptr, ptr]),
     "pyglm_means": (c_int, [ptr, c_int, ptr, c_int, c_int, c_int, c_int, ptr, c_int, ptr]),
     "pyglm_pg_draw": (c_int, [ptr, c_int, c_ll, c_int, ptr, c_int, c_ull, c_uint, c_ll, c_int, c_int, ptr]),
+    "pyglm_pg_draw_ws_bytes": (size_t, [c_ll, c_int]),
+    "pyglm_pg_draw_ws": (c_int, [ptr, c_int, c_ll, c_int, ptr, c_int, c_ull, c_uint, c_ll, c_int, c_int, ptr, size_t,
+                                 ptr]),
     "pyglm_philox_uniforms": (c_int, [c_ull, c_uint, c_ull, c_int, c_int, ptr, ptr]),
     "pyglm_gram_tiles": (c_int, [c_int, c_int, ptr, c_int]),
     "pyglm_gram_slabs": (c_int, [c_int, c_int, c_int]),

@@ -46,6 +46,23 @@ struct PhiloxStream {
         uint32_t a = u32(), b = u32();
         return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
     }
+    static __device__ __forceinline__ double to_unif(uint32_t a, uint32_t b) {
+        return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+    }
+    // The next two uniforms of the stream (the same values as two unif() calls) with ONE unconditional block
+    // evaluation: between uniforms `have` is 0 or 2, so the pair is either a whole new block or the last two words
+    // of the current block and the first two of the next.  Lanes of a warp whose streams are at different offsets
+    // still evaluate the block function together.  have += 2 afterwards hands the second uniform back (which can
+    // leave a whole block unread, have == 4: the one case that needs no evaluation).
+    __device__ __forceinline__ void unif2(double& ua, double& ub) {
+        const bool half = (have == 2);
+        const uint32_t p2 = o2, p3 = o3;
+        if (have != 4) refill();
+        ua = half ? to_unif(p2, p3) : to_unif(o0, o1);
+        ub = half ? to_unif(o0, o1) : to_unif(o2, o3);
+        have = half ? 2 : 0;
+    }
+    __device__ __forceinline__ void skip_block() { c3 += 1; have = 0; }
     __device__ __forceinline__ double expon() { return -log1p(-unif()); }
     // square of a standard normal (Box-Muller, cosine branch)
     __device__ __forceinline__ double norm_sq() {

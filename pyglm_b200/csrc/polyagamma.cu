@@ -209,6 +209,149 @@ pg_draw_kernel(const double* __restrict__ psi, int ldpsi, long long T, int n_val
     }
 }
 
+// ---- branch-compacted two-pass form ("warp-coherent rejection") -----------------------------------------------
+// One thread per draw keeps only ~9 of 32 lanes busy: about half of the lanes propose from the exponential tail (3
+// uniforms, no loop), the others from the truncated inverse Gaussian (two nested rejection loops, >= 6 uniforms), and
+// a warp pays for both.  Because an element's stream is a pure function of (seed, call, element), a draw can be
+// resumed by ANY thread.  Pass 1 makes the proposal choice for every element with all lanes converged, finishes the
+// exponential-tail draws on the spot and appends the others to a list (small z from the front, large z -- the
+// other inverse-Gaussian sampler -- from the back; warp-aggregated atomics).  Pass 2 walks each list with every
+// lane of a warp inside the same sampler, re-deriving the element's stream (one extra Philox block).  Decisions,
+// uniforms consumed and values are those of pg1_draw, so the oracle stream test applies unchanged.
+__global__ void __launch_bounds__(256, 4)
+pg_pick_kernel(const double* __restrict__ psi, int ldpsi, long long T, int n_valid, int ld_out,
+               unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
+               double* __restrict__ omega, unsigned* __restrict__ counts, unsigned* __restrict__ list,
+               unsigned capacity) {
+    const long long total = T * (long long)n_valid;
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    // rows of 32 consecutive elements, the same trip count for every lane of a warp (full-mask ballots below)
+    for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31u); base < total;
+         base += (long long)gridDim.x * blockDim.x) {
+        const long long idx = base + lane;
+        int kind = 0;                                         // 0: done here, 1: small-z IG, 2: large-z IG
+        if (idx < total) {
+            const long long t = idx / n_valid;
+            const int j = (int)(idx - t * n_valid);
+            const double p = psi[t * ldpsi + j];
+            PgRng r;
+            r.s.seed(seed, call_id, (unsigned long long)((t_off + t) * (long long)n_total + n_off + j));
+            const double z = fabs(p) * 0.5;
+            const double fz = 0.125 * PG_PI * PG_PI + 0.5 * z * z;
+            if (pg_pick_texpon(r.unif(), z, fz)) {
+                const double X = PG_T + r.expon() / fz;
+                omega[t * ld_out + j] = pg_series(X, r.unif()) ? 0.25 * X : pg1_draw(p, r);
+            } else {
+                kind = (PG_T_RECIP > z) ? 1 : 2;
+            }
+        }
+        const unsigned m1 = __ballot_sync(0xffffffffu, kind == 1), m2 = __ballot_sync(0xffffffffu, kind == 2);
+        unsigned b1 = 0, b2 = 0;
+        if (lane == 0) {
+            if (m1) b1 = atomicAdd(&counts[0], (unsigned)__popc(m1));
+            if (m2) b2 = atomicAdd(&counts[1], (unsigned)__popc(m2));
+        }
+        b1 = __shfl_sync(0xffffffffu, b1, 0);
+        b2 = __shfl_sync(0xffffffffu, b2, 0);
+        if (kind == 1) list[b1 + __popc(m1 & lt)] = (unsigned)idx;
+        else if (kind == 2) list[capacity - 1u - (b2 + __popc(m2 & lt))] = (unsigned)idx;
+    }
+}
+
+// Pass 2, small z (z < 1/t): the truncated inverse Gaussian by rejection from the tail of 1/E^2 -- two nested
+// rejection loops in pg_rtigauss.  With one list entry per thread a warp waits for its slowest lane (the maximum of
+// 32 geometric trip counts).  Here the loops are flattened into one step per iteration -- a pair trial (E1, E2),
+// and, when it is accepted, the alpha test and the series test -- and a lane that finishes a draw takes the next
+// entry of its warp's contiguous chunk of the list at once (ballot + popc, no atomics), so every lane does a pair
+// trial in every iteration until the chunk runs dry.  Each step's two uniforms come from unif2(): one block
+// evaluation per step, executed by all lanes together whatever their stream offsets.  Block 0 of a listed
+// element's stream (the proposal-choice uniform and the first, never tested, alpha uniform) is skipped, not computed.
+__global__ void __launch_bounds__(256, 4)
+pg_ig_small_kernel(const double* __restrict__ psi, int ldpsi, int n_valid, int ld_out,
+                   unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
+                   double* __restrict__ omega, const unsigned* __restrict__ counts,
+                   const unsigned* __restrict__ list) {
+    const unsigned long long count = counts[0];
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const unsigned long long warp = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long n_warps = (gridDim.x * (unsigned long long)blockDim.x) >> 5;
+    const unsigned long long per = (count + n_warps - 1) / n_warps;
+    unsigned long long next = warp * per < count ? warp * per : count;
+    const unsigned long long end = next + per < count ? next + per : count;
+    bool active = false;
+    PgRng r;
+    double z = 0.0, p = 0.0;
+    long long out = 0;
+    for (;;) {
+        const unsigned want = __ballot_sync(0xffffffffu, !active);
+        if (want) {
+            const unsigned long long mine = next + __popc(want & lt);
+            if (!active && mine < end) {
+                const unsigned idx = list[mine];
+                const long long t = idx / (unsigned)n_valid;
+                const int j = (int)(idx - (unsigned)t * (unsigned)n_valid);
+                p = psi[t * ldpsi + j];
+                z = fabs(p) * 0.5;
+                out = t * ld_out + j;
+                r.s.seed(seed, call_id, (unsigned long long)((t_off + t) * (long long)n_total + n_off + j));
+                r.s.skip_block();
+                active = true;
+            }
+            next += __popc(want);
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
+            double u1, u2;
+            r.s.unif2(u1, u2);
+            const float e1 = pg_expon32(u1), e2 = pg_expon32(u2);
+            const float lhs = e1 * e1, rhs = 3.125f * e2;
+            int c = pg_less32(rhs, lhs, fmaxf(lhs, rhs));      // rhs < lhs: reject the pair
+            bool reject;
+            if (c >= 0) reject = (c == 1);
+            else {
+                const double E1 = -d_log(1.0 - u1), E2 = -d_log(1.0 - u2);
+                reject = E1 * E1 > 2.0 * E2 / PG_T;
+            }
+            if (!reject) {
+                const double E1 = -d_log(1.0 - u1);
+                double X = 1.0 + E1 * PG_T;
+                X = PG_T / (X * X);
+                double ua, us;
+                r.s.unif2(ua, us);
+                const float al = __expf(-0.5f * (float)(z * z * X));
+                c = pg_less32(al, (float)ua, 1.0f);            // alpha < u: propose again
+                const bool again = (c >= 0) ? (c == 1) : (ua > d_exp(-0.5 * z * z * X));
+                if (again) {
+                    r.s.have += 2;                              // the series uniform was not drawn
+                } else {
+                    omega[out] = pg_series(X, us) ? 0.25 * X : pg1_draw(p, r);
+                    active = false;
+                }
+            }
+        }
+    }
+}
+
+template <bool LARGE>
+__global__ void __launch_bounds__(256, 4)
+pg_ig_kernel(const double* __restrict__ psi, int ldpsi, int n_valid, int ld_out,
+             unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
+             double* __restrict__ omega, const unsigned* __restrict__ counts, const unsigned* __restrict__ list,
+             unsigned capacity) {
+    const unsigned count = counts[LARGE ? 1 : 0];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const unsigned idx = LARGE ? list[capacity - 1u - i] : list[i];
+        const long long t = idx / (unsigned)n_valid;
+        const int j = (int)(idx - (unsigned)t * (unsigned)n_valid);
+        const double p = psi[t * ldpsi + j];
+        PgRng r;
+        r.s.seed(seed, call_id, (unsigned long long)((t_off + t) * (long long)n_total + n_off + j));
+        (void)r.unif();                                       // the proposal-choice uniform, spent in pass 1
+        const double X = pg_rtigauss(fabs(p) * 0.5, r);
+        omega[t * ld_out + j] = pg_series(X, r.unif()) ? 0.25 * X : pg1_draw(p, r);
+    }
+}
+
 __global__ void philox_unif_kernel(unsigned long long seed, unsigned call_id, unsigned long long elem0, int n_elem,
                                    int count, double* __restrict__ out) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,6 +375,38 @@ extern "C" int pyglm_pg_draw(const double* psi, int ldpsi, long long T, int n_va
     long long total = T * (long long)n_valid;
     int blocks = (int)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
     pg_draw_kernel<<<blocks, 256, 0, stream>>>(psi, ldpsi, T, n_valid, ld_out, seed, call_id, t_off, n_off, n_total, omega);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
+// The same draws through the branch-compacted two-pass kernels.  workspace: pyglm_pg_draw_ws_bytes(T, n_valid) bytes
+// of device memory (16 B of counters + one 32-bit element index per draw), contents irrelevant on entry.  Falls back
+// to the one-pass kernel when the element indices do not fit 32 bits or the workspace is too small.
+extern "C" size_t pyglm_pg_draw_ws_bytes(long long T, int n_valid) {
+    return 16 + 4 * (size_t)(T > 0 ? T : 0) * (size_t)(n_valid > 0 ? n_valid : 0);
+}
+
+extern "C" int pyglm_pg_draw_ws(const double* psi, int ldpsi, long long T, int n_valid, double* omega, int ld_out,
+                                unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
+                                void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(psi && omega, "pyglm_pg_draw_ws: null pointer");
+    PYGLM_CHECK_ARG(T > 0 && n_valid > 0 && ldpsi >= n_valid && ld_out >= n_valid && n_total >= n_off + n_valid,
+                    "pyglm_pg_draw_ws: bad shape (T=%lld n=%d ldpsi=%d ld_out=%d n_off=%d n_total=%d)", T, n_valid, ldpsi, ld_out, n_off, n_total);
+    const long long total = T * (long long)n_valid;
+    if (!workspace || total >= 0xffffffffLL || workspace_bytes < pyglm_pg_draw_ws_bytes(T, n_valid))
+        return pyglm_pg_draw(psi, ldpsi, T, n_valid, omega, ld_out, seed, call_id, t_off, n_off, n_total, stream);
+    unsigned* counts = (unsigned*)workspace;
+    unsigned* list = counts + 4;
+    PYGLM_CUDA(cudaMemsetAsync(counts, 0, 16, stream));
+    const int blocks = (int)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
+    pg_pick_kernel<<<blocks, 256, 0, stream>>>(psi, ldpsi, T, n_valid, ld_out, seed, call_id, t_off, n_off, n_total,
+                                               omega, counts, list, (unsigned)total);
+    PYGLM_LAUNCH_CHECK();
+    pg_ig_small_kernel<<<blocks, 256, 0, stream>>>(psi, ldpsi, n_valid, ld_out, seed, call_id, t_off, n_off, n_total,
+                                                   omega, counts, list);
+    PYGLM_LAUNCH_CHECK();
+    pg_ig_kernel<true><<<blocks, 256, 0, stream>>>(psi, ldpsi, n_valid, ld_out, seed, call_id, t_off, n_off, n_total,
+                                                   omega, counts, list, (unsigned)total);
     PYGLM_LAUNCH_CHECK();
     return PYGLM_OK;
 }

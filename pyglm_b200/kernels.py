@@ -5,6 +5,7 @@ hand-written sm_100a kernels in pyglm_b200/csrc.  There is no fallback: construc
 without a B200-class device, or without the built library, raises.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -121,9 +122,19 @@ class CudaKernels(object):
 
     # ------------------------------------------------------------------ (2) Polya-gamma
     def pg_draw(self, psi, n_valid, omega, seed, call_id, t_off, n_off, n_total):
+        """omega ~ PG(1, psi).  Default: the branch-compacted two-pass kernels (same draws, element by element, as
+        the one-pass kernel, which PYGLM_PG_VARIANT=1 selects for comparison)."""
         T = psi.shape[0]
-        self._call("pyglm_pg_draw", self._p(psi), psi.shape[1], T, n_valid, self._p(omega), omega.shape[1],
-                   seed, call_id, t_off, n_off, n_total, self._stream())
+        if os.environ.get("PYGLM_PG_VARIANT", "2") == "1":
+            self._call("pyglm_pg_draw", self._p(psi), psi.shape[1], T, n_valid, self._p(omega), omega.shape[1],
+                       seed, call_id, t_off, n_off, n_total, self._stream())
+            return omega
+        need = int(self.lib.pyglm_pg_draw_ws_bytes(T, n_valid))
+        ws = getattr(self, "_pg_ws", None)
+        if ws is None or ws.numel() < need:
+            ws = self._pg_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._call("pyglm_pg_draw_ws", self._p(psi), psi.shape[1], T, n_valid, self._p(omega), omega.shape[1],
+                   seed, call_id, t_off, n_off, n_total, self._p(ws), ws.numel(), self._stream(), launches=3)
         return omega
 
     def philox_uniforms(self, seed, call_id, elem0, n_elem, count):

@@ -170,6 +170,26 @@ def test_pg_draws_match_oracle_stream(K):
     assert np.median(rel) < 1e-14
 
 
+def test_pg_two_pass_equals_one_pass(K, monkeypatch):
+    """The branch-compacted kernels (pyglm_pg_draw_ws, the default) resume each element's stream in another thread:
+    the draws must be those of the one-pass kernel bit for bit, for every proposal branch, ragged sizes included."""
+    from pyglm_b200.kernels import pad_ldn
+    for T, n, scale in ((1, 1, 1.0), (37, 3, 2.0), (5001, 7, 3.0), (20000, 33, 1.0)):
+        rng = np.random.default_rng(T)
+        psi = np.zeros((T, pad_ldn(n)))
+        psi[:, :n] = rng.standard_normal((T, n)) * scale - 2.0
+        psi[0, 0] = 40.0
+        psi_d = K.to_device(psi)
+        out = {}
+        for variant in ("1", "2"):
+            monkeypatch.setenv("PYGLM_PG_VARIANT", variant)
+            om = K.zeros(T, pad_ldn(n)) - 1.0
+            K.pg_draw(psi_d, n, om, 5, 11, 123, 2, n + 4)
+            out[variant] = om.cpu().numpy()
+        assert np.all(out["2"][:, :n] > 0) and np.all(out["2"][:, n:] == -1.0)
+        assert np.array_equal(out["1"], out["2"])
+
+
 @pytest.mark.parametrize("z", [0.0, 0.5, 2.0, 5.0, 12.0])
 def test_pg_moments(K, z):
     from pyglm_b200.kernels import pad_ldn
