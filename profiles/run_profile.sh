@@ -15,7 +15,7 @@ python profiles/profile_sweep.py --int8 > gpurun_out/${TAG}_int8_peak.json 2>&1
 cat gpurun_out/${TAG}_int8_peak.json
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
     python profiles/profile_sweep.py --sweeps 2 > gpurun_out/${TAG}_launches.log 2>&1
-for k in gram_tc_kernel pg_draw_kernel spike_slab activation_kernel; do
+for k in ${KERNELS:-gram_tc_kernel pg_pick_kernel pg_ig_small_kernel spike_slab activation_kernel}; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_$k \
       python profiles/profile_sweep.py --sweeps 2 > gpurun_out/${TAG}_prof_$k.log 2>&1
   ncu -i gpurun_out/${TAG}_prof_$k.ncu-rep --page details > gpurun_out/${TAG}_ncu_$k.txt 2>&1

@@ -231,8 +231,8 @@ pg_pick_kernel(const double* __restrict__ psi, int ldpsi, long long T, int n_val
         const long long idx = base + lane;
         int kind = 0;                                         // 0: done here, 1: small-z IG, 2: large-z IG
         if (idx < total) {
-            const long long t = idx / n_valid;
-            const int j = (int)(idx - t * n_valid);
+            const long long t = (unsigned)idx / (unsigned)n_valid;          // total < 2^32 on this path
+            const int j = (int)((unsigned)idx - (unsigned)t * (unsigned)n_valid);
             const double p = psi[t * ldpsi + j];
             PgRng r;
             r.s.seed(seed, call_id, (unsigned long long)((t_off + t) * (long long)n_total + n_off + j));
