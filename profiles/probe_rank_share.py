@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--gram", default="auto")
     ap.add_argument("--shard", default="neuron")
     ap.add_argument("--pipeline", type=int, default=1)
+    ap.add_argument("--network", default=None, help="class in pyglm_b200.networks, e.g. NIWLatentDistanceNetwork")
     a = ap.parse_args()
     cfg = CONFIGS[a.config]
     N, B, L, T = cfg["N"], cfg["B"], cfg["L"], cfg["T"]
@@ -65,8 +66,12 @@ def main():
     for world in [int(w) for w in a.worlds.split(",")]:
         np.random.seed(0)
         comm = FakeComm(world, 0) if world > 1 else None
+        net = None
+        if a.network:
+            from pyglm_b200 import networks
+            net = getattr(networks, a.network)(N, B)
         model = SparseBernoulliGLM(N, basis=cosine_basis(B=B, L=L) / L, regression_kwargs=dict(S_w=10.0, mu_b=-2.),
-                                   seed=1234, gram=a.gram, comm=comm, shard=a.shard)
+                                   seed=1234, gram=a.gram, comm=comm, shard=a.shard, network=net)
         model.add_data(Y, host_X=False)
         model.engine.pipeline = bool(a.pipeline)
         if world > 1 and a.shard == "time":
@@ -86,7 +91,11 @@ def main():
         torch.cuda.synchronize()
         ph = eng.phase_ms()
         ms = e0.elapsed_time(e1) / a.steps
-        print(json.dumps(dict(world=world, shard=a.shard, pipeline=a.pipeline, n_loc=eng.scan_hi - eng.scan_lo, ms_per_sweep_e2e=ms, phases=ph,
+        import time
+        t0 = time.perf_counter()
+        model.resample_network()
+        host_net_ms = (time.perf_counter() - t0) * 1e3
+        print(json.dumps(dict(world=world, shard=a.shard, network=a.network or "NIWSparseNetwork", host_network_step_ms=host_net_ms, pipeline=a.pipeline, n_loc=eng.scan_hi - eng.scan_lo, ms_per_sweep_e2e=ms, phases=ph,
                               other_ms=ms - sum(v for k, v in ph.items() if not k.startswith("gram_")),
                               density=float(model.adjacency.mean()))), flush=True)
         del model, eng

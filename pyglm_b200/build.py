@@ -41,7 +41,7 @@ def build_library(force=False, verbose=False):
     if not force and not _stale():
         return LIBPATH
     from concurrent.futures import ThreadPoolExecutor
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(os.path.dirname(HERE), "build", "obj")     # git- and gpurun-ignored
     os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
     headers = glob.glob(os.path.join(CSRC, "*.cuh"))

@@ -328,6 +328,8 @@ class HierarchicalNonlinearAutoregressiveModel(NonlinearAutoregressiveModel):
             # every rank -- no per-sweep host collective on the critical path between two scans.  The chain is the
             # one a single process with rank 0's seed would produce.
             np.random.set_state(comm.broadcast_object(np.random.get_state() if comm.rank == 0 else None))
+            # priors that carry latent state from sweep to sweep (block labels, locations) also start from rank 0's
+            net.set_state(comm.broadcast_object(net.get_state() if comm.rank == 0 else None))
             self._rng_synced = True
         net.resample((self.adjacency, self.weights))
         sigma_W, mu_W, rho = net.sigma_W, net.mu_W, net.rho

@@ -21,15 +21,19 @@ def _free_port():
     return p
 
 
-def _chain(comm, shard, n_sweeps=3, gram="auto"):
+def _chain(comm, shard, n_sweeps=3, gram="auto", prior=None):
+    from pyglm_b200 import networks
     from pyglm_b200.models import SparseBernoulliGLM
     from pyglm_b200.utils.basis import cosine_basis
     N, B, L, T = 10, 2, 20, 5000
     basis = cosine_basis(B, L) / L
     Y = (np.random.default_rng(3).random((T, N)) < 0.08).astype(np.float64)
+    # a prior with latent state is built from a rank-dependent seed: the model has to hand out rank 0's
+    np.random.seed(0 if prior is None else 100 + comm.rank)
+    net = None if prior is None else getattr(networks, prior)(N, B)
     np.random.seed(0)
-    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=77, comm=comm,
-                           shard=shard, gram=gram)
+    m = SparseBernoulliGLM(N, basis=basis, network=net, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=77,
+                           comm=comm, shard=shard, gram=gram)
     m.add_data(Y, host_X=False)
     lls = []
     for _ in range(n_sweeps):
@@ -38,7 +42,7 @@ def _chain(comm, shard, n_sweeps=3, gram="auto"):
     return m.adjacency, m.weights, m.biases, np.array(lls)
 
 
-def _worker(rank, world, port, shard, out, gram="auto"):
+def _worker(rank, world, port, shard, out, gram="auto", prior=None):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -47,7 +51,7 @@ def _worker(rank, world, port, shard, out, gram="auto"):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from pyglm_b200.distributed import Comm
-        A, W, b, lls = _chain(Comm(), shard, gram=gram)
+        A, W, b, lls = _chain(Comm(), shard, gram=gram, prior=prior)
         if rank == 0:
             np.savez(out, A=A, W=W, b=b, lls=lls)
     finally:
@@ -86,3 +90,20 @@ def test_two_gpu_time_sharded_tensor_core_gram(tmp_path):
     np.testing.assert_allclose(g["W"], W0, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(g["b"], b0, rtol=1e-9)
     np.testing.assert_allclose(g["lls"], lls0, rtol=1e-11)
+
+
+@pytest.mark.parametrize("prior", ["NIWStochasticBlockNetwork", "NIWLatentDistanceNetwork"])
+def test_two_gpu_chain_with_stateful_network_prior(tmp_path, prior):
+    """Adjacency priors that carry latent state (block labels, locations): every rank draws the host step itself from
+    rank 0's numpy stream, starting from rank 0's network state, so the 2-GPU chain is the single-GPU chain."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from pyglm_b200.distributed import Comm
+    A0, W0, b0, lls0 = _chain(Comm(), "neuron", prior=prior)
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_worker, args=(2, _free_port(), "neuron", out, "auto", prior), nprocs=2, join=True)
+    g = np.load(out)
+    assert np.array_equal(g["A"], A0)
+    np.testing.assert_allclose(g["W"], W0, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(g["lls"], lls0, rtol=1e-9)
