@@ -4,7 +4,7 @@ other strongly, blocks are not connected.  The regressions run on the GPU; the b
 connection probabilities and the NIW weight prior are resampled on the host after every sweep and fed back as the
 inclusion prior rho of the spike-and-slab scan (pyglm/models.py:228-236).
 
-    python examples/block_network.py [--N 16] [--T 20000] [--sweeps 60] [--prior block|distance|beta_bernoulli]
+    python examples/block_network.py [--N 16] [--T 200000] [--sweeps 100] [--prior block|distance|beta_bernoulli]
 """
 import argparse
 import os
@@ -19,9 +19,12 @@ from pyglm_b200.utils.basis import cosine_basis  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--N", type=int, default=16)
-ap.add_argument("--T", type=int, default=20000)
-ap.add_argument("--sweeps", type=int, default=60)
+ap.add_argument("--T", type=int, default=200000)
+ap.add_argument("--sweeps", type=int, default=100)
 ap.add_argument("--prior", default="block", choices=["block", "distance", "beta_bernoulli"])
+ap.add_argument("--weights", default="fixed", choices=["fixed", "niw"],
+                help="fixed N(0, 1) slab, or the learned NIW slab (under which weak and absent connections are hard "
+                     "to tell apart, so the graph -- and with it the block structure -- stays diffuse)")
 args = ap.parse_args()
 np.random.seed(0)
 N, T, B, L = args.N, args.T, 1, 50
@@ -39,9 +42,9 @@ for n in range(N):
 _, Y = true_model.generate(T=T, keep=True)
 print("simulated %d bins x %d neurons, mean rate %.3f" % (T, N, Y.mean()))
 
-net = dict(block=lambda: networks.NIWStochasticBlockNetwork(N, B, C=2),
-           distance=lambda: networks.NIWLatentDistanceNetwork(N, B, dim=2),
-           beta_bernoulli=lambda: networks.NIWBetaBernoulliNetwork(N, B))[args.prior]()
+cls = dict(block="StochasticBlockNetwork", distance="LatentDistanceNetwork", beta_bernoulli="BetaBernoulliNetwork")
+cls = getattr(networks, ("FixedMean" if args.weights == "fixed" else "NIW") + cls[args.prior])
+net = cls(N, B, **(dict(C=2) if args.prior == "block" else dict(dim=2) if args.prior == "distance" else {}))
 model = SparseBernoulliGLM(N, basis=basis, network=net, regression_kwargs=dict(S_w=1.0, mu_b=-3.0))
 model.add_data(Y)
 rho_mean = np.zeros((N, N))

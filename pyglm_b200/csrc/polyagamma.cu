@@ -223,17 +223,34 @@ pg_pick_kernel(const double* __restrict__ psi, int ldpsi, long long T, int n_val
                unsigned long long seed, unsigned call_id, long long t_off, int n_off, int n_total,
                double* __restrict__ omega, unsigned* __restrict__ counts, unsigned* __restrict__ list,
                unsigned capacity) {
-    const long long total = T * (long long)n_valid;
-    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    // rows of 32 consecutive elements, the same trip count for every lane of a warp (full-mask ballots below)
-    for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31u); base < total;
-         base += (long long)gridDim.x * blockDim.x) {
-        const long long idx = base + lane;
+    // List space is claimed once per CTA iteration (256 elements), not once per warp row: both counters live in
+    // one L2 sector, and same-address atomics retire about one per L2 clock -- at two per warp row (1.25 M at
+    // cfg3) that serialisation alone was most of this kernel's time (ncu r01m: long-scoreboard 69 % of the stall
+    // cycles, issue slots 40 % busy).  Buffers alternate with the iteration parity, so two barriers per iteration do.
+    __shared__ unsigned s_cnt[2][2][8], s_base[2][2];
+    const unsigned total = (unsigned)(T * (long long)n_valid);            // < 2^32 - 1 on this path
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned par = 0;
+    // same trip count for every thread of a CTA (barriers and full-mask ballots below); psi is fetched one
+    // iteration ahead
+    unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x;
+    double p_next = 0.0;
+    if (base + threadIdx.x < total) {
+        const unsigned i0 = (unsigned)base + threadIdx.x, t0 = i0 / (unsigned)n_valid;
+        p_next = psi[(long long)t0 * ldpsi + (i0 - t0 * (unsigned)n_valid)];
+    }
+    for (; base < total; base += stride, par ^= 1u) {
+        const unsigned long long idx = base + threadIdx.x;
+        const double p = p_next;
+        if (idx + stride < total) {
+            const unsigned i1 = (unsigned)(idx + stride), t1 = i1 / (unsigned)n_valid;
+            p_next = psi[(long long)t1 * ldpsi + (i1 - t1 * (unsigned)n_valid)];
+        }
         int kind = 0;                                         // 0: done here, 1: small-z IG, 2: large-z IG
         if (idx < total) {
-            const long long t = (unsigned)idx / (unsigned)n_valid;          // total < 2^32 on this path
+            const long long t = (unsigned)idx / (unsigned)n_valid;
             const int j = (int)((unsigned)idx - (unsigned)t * (unsigned)n_valid);
-            const double p = psi[t * ldpsi + j];
             PgRng r;
             r.s.seed(seed, call_id, (unsigned long long)((t_off + t) * (long long)n_total + n_off + j));
             const double z = fabs(p) * 0.5;
@@ -246,15 +263,21 @@ pg_pick_kernel(const double* __restrict__ psi, int ldpsi, long long T, int n_val
             }
         }
         const unsigned m1 = __ballot_sync(0xffffffffu, kind == 1), m2 = __ballot_sync(0xffffffffu, kind == 2);
-        unsigned b1 = 0, b2 = 0;
-        if (lane == 0) {
-            if (m1) b1 = atomicAdd(&counts[0], (unsigned)__popc(m1));
-            if (m2) b2 = atomicAdd(&counts[1], (unsigned)__popc(m2));
+        if (lane == 0) { s_cnt[par][0][warp] = __popc(m1); s_cnt[par][1][warp] = __popc(m2); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            unsigned tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_cnt[par][threadIdx.x][w];
+            s_base[par][threadIdx.x] = tot ? atomicAdd(&counts[threadIdx.x], tot) : 0u;
         }
-        b1 = __shfl_sync(0xffffffffu, b1, 0);
-        b2 = __shfl_sync(0xffffffffu, b2, 0);
-        if (kind == 1) list[b1 + __popc(m1 & lt)] = (unsigned)idx;
-        else if (kind == 2) list[capacity - 1u - (b2 + __popc(m2 & lt))] = (unsigned)idx;
+        __syncthreads();
+        if (kind) {
+            unsigned off = s_base[par][kind - 1];
+            for (unsigned w = 0; w < warp; ++w) off += s_cnt[par][kind - 1][w];
+            if (kind == 1) list[off + __popc(m1 & lt)] = (unsigned)idx;
+            else list[capacity - 1u - (off + __popc(m2 & lt))] = (unsigned)idx;
+        }
     }
 }
 

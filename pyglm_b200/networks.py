@@ -470,3 +470,18 @@ class NIWStochasticBlockNetwork(_StochasticBlockAdjacencyMixin, _IndependentGaus
 
 class NIWLatentDistanceNetwork(_LatentDistanceAdjacencyMixin, _IndependentGaussianMixin):
     pass
+
+
+# the same adjacency priors over a FIXED Gaussian weight prior (mu, sigma, mu_self, sigma_self as in
+# FixedMeanSparseNetwork): with the slab held fixed, absent connections are told apart by the marginal likelihood
+# alone, which is what lets the block / distance structure of the graph be learned from short recordings
+class FixedMeanBetaBernoulliNetwork(_IndependentBernoulliMixin, _FixedWeightsMixin):
+    pass
+
+
+class FixedMeanStochasticBlockNetwork(_StochasticBlockAdjacencyMixin, _FixedWeightsMixin):
+    pass
+
+
+class FixedMeanLatentDistanceNetwork(_LatentDistanceAdjacencyMixin, _FixedWeightsMixin):
+    pass

@@ -172,3 +172,17 @@ def test_latent_distance_recovers_planted_geometry():
     other = NIWLatentDistanceNetwork(N, B, dim=2)
     other.set_state(net.get_state())
     assert np.array_equal(other.rho, net.rho)
+
+
+def test_fixed_weight_combinations():
+    from pyglm_b200 import networks
+    N, B = 6, 2
+    np.random.seed(7)
+    A = np.random.rand(N, N) < 0.5
+    for name, kw in (("FixedMeanBetaBernoulliNetwork", {}), ("FixedMeanStochasticBlockNetwork", dict(C=3)),
+                     ("FixedMeanLatentDistanceNetwork", dict(dim=3))):
+        net = getattr(networks, name)(N, B, mu=0.5, sigma=2.0, mu_self=-1.0, sigma_self=0.5, **kw)
+        net.resample((A, _weights(N, B)))
+        assert np.all(net.mu_W[0, 1] == 0.5) and np.all(net.mu_W[2, 2] == -1.0)
+        assert np.array_equal(net.sigma_W[0, 1], 2.0 * np.eye(B)) and np.array_equal(net.sigma_W[3, 3], 0.5 * np.eye(B))
+        assert net.rho.shape == (N, N) and np.all((net.rho > 0) & (net.rho < 1))
