@@ -47,6 +47,13 @@ cls = getattr(networks, ("FixedMean" if args.weights == "fixed" else "NIW") + cl
 net = cls(N, B, **(dict(C=2) if args.prior == "block" else dict(dim=2) if args.prior == "distance" else {}))
 model = SparseBernoulliGLM(N, basis=basis, network=net, regression_kwargs=dict(S_w=1.0, mu_b=-3.0))
 model.add_data(Y)
+# Start-up: a few sweeps of the regressions alone (inclusion prior 1/2), then labels / locations initialised on the
+# graph found so far.  Attached from the first sweep, the prior sees the all-ones initial adjacency, puts every
+# neuron into one block and leaves that mode only slowly.
+for _ in range(args.sweeps // 4):
+    model.resample_regressions()
+for _ in range(25):
+    net.resample((model.adjacency, model.weights))
 rho_mean = np.zeros((N, N))
 for itr in range(args.sweeps):
     if itr == args.sweeps // 2:
