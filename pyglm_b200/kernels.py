@@ -130,9 +130,12 @@ class CudaKernels(object):
                        seed, call_id, t_off, n_off, n_total, self._stream())
             return omega
         need = int(self.lib.pyglm_pg_draw_ws_bytes(T, n_valid))
-        ws = getattr(self, "_pg_ws", None)
+        # one workspace per stream: two draws enqueued on different streams must not share their index lists
+        cache = self.__dict__.setdefault("_pg_ws", {})
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = cache.get(key)
         if ws is None or ws.numel() < need:
-            ws = self._pg_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            ws = cache[key] = torch.empty(need, dtype=torch.uint8, device=self.device)
         self._call("pyglm_pg_draw_ws", self._p(psi), psi.shape[1], T, n_valid, self._p(omega), omega.shape[1],
                    seed, call_id, t_off, n_off, n_total, self._p(ws), ws.numel(), self._stream(), launches=3)
         return omega

@@ -30,14 +30,19 @@ def _problem():
     return N, B, basis, Y
 
 
-def _run_chain(comm, shard, n_sweeps=2):
-    """Build the model on this rank and run a short chain; identical host RNG seeding on every rank."""
+def _run_chain(comm, shard, n_sweeps=2, prior=None):
+    """Build the model on this rank and run a short chain; identical host RNG seeding on every rank -- except for the
+    network prior when one with latent state is asked for: it is built from a rank-dependent seed, and the model
+    must hand out rank 0's state."""
+    from pyglm_b200 import networks
     from pyglm_b200.engine import GibbsEngine
     from pyglm_b200.models import SparseBernoulliGLM
     from tests.oracle_kernels import OracleKernels
     N, B, basis, Y = _problem()
+    np.random.seed(100 + comm.rank)
+    net = None if prior is None else getattr(networks, prior)(N, B)
     np.random.seed(0)
-    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0, rho=0.4), seed=77)
+    m = SparseBernoulliGLM(N, basis=basis, network=net, regression_kwargs=dict(S_w=10.0, mu_b=-2.0, rho=0.4), seed=77)
     m._engine = GibbsEngine(N, B, kernels=OracleKernels(), seed=77, comm=comm, shard=shard)
     m.add_data(Y, host_X=False)
     lls = []
@@ -47,14 +52,14 @@ def _run_chain(comm, shard, n_sweeps=2):
     return m.adjacency, m.weights, m.biases, np.array(lls), m.means[0] if shard == "neuron" else None
 
 
-def _worker(rank, world, port, shard, out):
+def _worker(rank, world, port, shard, out, prior=None, n_sweeps=2):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from pyglm_b200.distributed import Comm
-        A, W, b, lls, mu = _run_chain(Comm(), shard)
+        A, W, b, lls, mu = _run_chain(Comm(), shard, n_sweeps=n_sweeps, prior=prior)
         if rank == 0:
             np.savez(out, A=A, W=W, b=b, lls=lls, mu=mu if mu is not None else np.zeros(0))
         # every rank must end with the same state
@@ -80,6 +85,20 @@ def test_two_rank_sweep_matches_single_process(tmp_path, shard):
     np.testing.assert_allclose(g["lls"], lls0, rtol=1e-12)
     if shard == "neuron":
         np.testing.assert_allclose(g["mu"], mu0, rtol=1e-12)
+
+
+@pytest.mark.parametrize("prior", ["NIWStochasticBlockNetwork", "NIWLatentDistanceNetwork"])
+def test_two_rank_chain_with_stateful_network_prior(tmp_path, prior):
+    """Block labels / latent locations persist from sweep to sweep: all ranks start from rank 0's network state and
+    draw the host step from rank 0's numpy stream, so the sharded chain is the single-process chain."""
+    from pyglm_b200.distributed import Comm
+    A0, W0, b0, lls0, _ = _run_chain(Comm(), "neuron", n_sweeps=4, prior=prior)
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_worker, args=(2, _free_port(), "neuron", out, prior, 4), nprocs=2, join=True)
+    g = np.load(out)
+    assert np.array_equal(g["A"], A0)
+    np.testing.assert_allclose(g["W"], W0, rtol=0, atol=0)
+    np.testing.assert_allclose(g["lls"], lls0, rtol=1e-12)
 
 
 def test_partitions():
