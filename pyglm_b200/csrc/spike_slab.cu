@@ -1578,7 +1578,9 @@ int launch_fast(const SpikeSlabArgs& A, cudaStream_t stream) {
     static int la_env = -1;
     if (la_env < 0) { const char* e = getenv("PYGLM_SS_LOOKAHEAD"); la_env = e ? atoi(e) : 8; }
     const size_t per_slot = (size_t)2 * Dpad_ * B * sizeof(double);
-    int G = (smem < 227 * 1024) ? (int)((227 * 1024 - smem) / per_slot) : 0;
+    // MINB = 2: two CTAs (two neurons) share an SM -- half of its shared memory each, so a shorter lookahead table
+    const size_t budget = (MINB >= 2 ? 113 : 227) * 1024;
+    int G = (smem < budget) ? (int)((budget - smem) / per_slot) : 0;
     if (G > 16 / B) G = 16 / B;
     if (G > 8) G = 8;
     if (G > la_env) G = la_env;
@@ -1586,7 +1588,7 @@ int launch_fast(const SpikeSlabArgs& A, cudaStream_t stream) {
     smem += (size_t)G * per_slot;
     SpikeSlabArgs A2 = A;
     A2.la_G = G;
-    if (smem > 227 * 1024) {
+    if (smem > budget) {
         pyglm_set_error("pyglm_spike_slab_update: N*B=%d too large for the shared-memory state (%zu bytes)", A.N * B, smem);
         return PYGLM_ERR_INVALID;
     }
@@ -1619,8 +1621,14 @@ int launch_fast_variant(const SpikeSlabArgs& A, int variant, cudaStream_t stream
                                                                        // neuron on twice the SMs (the K x K passes are not what
                                                                        // bounds a step) -- kept for measurement only
         case 3: return launch_fast<B, 512, 1, false, 1>(A, stream);    // bordering build / draw (the first version; A/B runs)
-        default: return launch_fast<B, 512, 1, true, 1>(A, stream);    // one CTA per neuron
+        // two neurons per SM (co-resident CTAs hide each other's L2 latency; N = 200 then fits ONE wave of 148 SMs
+        // instead of 148 + 52): with 256 or 512 threads each.  Falls back to one CTA per SM when the state of a
+        // neuron does not fit half an SM's shared memory.
+        case 4: if constexpr (B == 2) { if (launch_fast<B, 256, 2, true, 1>(A, stream) == PYGLM_OK) return PYGLM_OK; } break;
+        case 5: if constexpr (B == 2) { if (launch_fast<B, 512, 2, true, 1>(A, stream) == PYGLM_OK) return PYGLM_OK; } break;
+        default: break;
     }
+    return launch_fast<B, 512, 1, true, 1>(A, stream);                 // one CTA per neuron, one per SM
 }
 
 // perm: Fisher-Yates permutation of 0..N-1 per local neuron; us: N uniforms; z: D normals keyed by coordinate.
