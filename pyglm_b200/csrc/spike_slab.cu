@@ -1621,11 +1621,12 @@ int launch_fast_variant(const SpikeSlabArgs& A, int variant, cudaStream_t stream
                                                                        // neuron on twice the SMs (the K x K passes are not what
                                                                        // bounds a step) -- kept for measurement only
         case 3: return launch_fast<B, 512, 1, false, 1>(A, stream);    // bordering build / draw (the first version; A/B runs)
-        // two neurons per SM (co-resident CTAs hide each other's L2 latency; N = 200 then fits ONE wave of 148 SMs
-        // instead of 148 + 52): with 256 or 512 threads each.  Falls back to one CTA per SM when the state of a
-        // neuron does not fit half an SM's shared memory.
+        // two neurons per SM, 256 threads each (N = 200 then fits ONE wave of 148 SMs instead of 148 + 52, at the
+        // price of a 2-slot lookahead table).  Measured at cfg3 (profiles/r01n_scan_variants.log): 4.5-5.2 ms
+        // against 3.6-4.4 ms -- the passes over P are L2-throughput bound, co-residency does not hide them; with 512
+        // threads and 64 registers (spills) 7-7.8 ms.  Kept for measurement only.  Falls back to one CTA per SM when
+        // the state of a neuron does not fit half an SM's shared memory.
         case 4: if constexpr (B == 2) { if (launch_fast<B, 256, 2, true, 1>(A, stream) == PYGLM_OK) return PYGLM_OK; } break;
-        case 5: if constexpr (B == 2) { if (launch_fast<B, 512, 2, true, 1>(A, stream) == PYGLM_OK) return PYGLM_OK; } break;
         default: break;
     }
     return launch_fast<B, 512, 1, true, 1>(A, stream);                 // one CTA per neuron, one per SM
