@@ -425,7 +425,10 @@ extern "C" int pyglm_pg_draw_ws(const double* psi, int ldpsi, long long T, int n
     pg_pick_kernel<<<blocks, 256, 0, stream>>>(psi, ldpsi, T, n_valid, ld_out, seed, call_id, t_off, n_off, n_total,
                                                omega, counts, list, (unsigned)total);
     PYGLM_LAUNCH_CHECK();
-    pg_ig_small_kernel<<<blocks, 256, 0, stream>>>(psi, ldpsi, n_valid, ld_out, seed, call_id, t_off, n_off, n_total,
+    // one resident wave (4 CTAs per SM): each warp then owns a long chunk of the list, and the idle tail at the end of
+    // a chunk -- lanes waiting for the warp's last draw -- is paid once per warp, not once per 8 entries per lane
+    const int small_blocks = blocks < 148 * 4 ? blocks : 148 * 4;
+    pg_ig_small_kernel<<<small_blocks, 256, 0, stream>>>(psi, ldpsi, n_valid, ld_out, seed, call_id, t_off, n_off, n_total,
                                                    omega, counts, list);
     PYGLM_LAUNCH_CHECK();
     pg_ig_kernel<true><<<blocks, 256, 0, stream>>>(psi, ldpsi, n_valid, ld_out, seed, call_id, t_off, n_off, n_total,
