@@ -6,9 +6,13 @@
 // with a private counter-based Philox4x32-10 stream keyed by (seed, call_id, global element index),
 // so draws do not depend on grid shape or on how neurons / time are sharded across GPUs, and match
 // the CPU oracle (oracle/pg_devroye.c, rng_kind 0) element by element.
-// Divergence: the outer loop accepts on its first proposal ~99.9% of the time and the series test
-// ends after one or two terms, so lanes of a warp stay converged except in the rare retry.
-// Algorithmic traffic: 8 B psi read + 8 B omega write per draw (HBM roofline).
+// Divergence: the outer loop accepts on its first proposal ~99.9% of the time and the series test ends
+// after one or two terms, but the two proposal samplers differ (3 uniforms and no loop against >= 6
+// uniforms and two nested rejection loops): one thread per draw (pg_draw_kernel) runs at 9 of 32 lanes.
+// The default path is therefore the branch-compacted two-pass form further down (pg_pick_kernel,
+// pg_ig_small_kernel, pg_ig_kernel), which produces the same draws.
+// Algorithmic traffic: 8 B psi read + 8 B omega write per draw (HBM roofline); the kernels
+// are bound by instruction issue (~900 thread-instructions per exact draw), not by bytes.
 #include "common.cuh"
 #include "philox.cuh"
 
