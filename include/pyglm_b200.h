@@ -76,9 +76,12 @@ int pyglm_weighted_gram(const double* Xp, int ldx, int T, const double* Om, int 
                         int i_base, double* workspace, pyglm_stream_t stream);
 
 /* (3') The same weighted Gram (pyglm/regression.py:251-256) on the tcgen05 tensor cores, for non-negative designs:
- * both operands are split into S radix-256 digits (digit 0 unsigned, the rest signed round-to-nearest), every
- * digit product of order a+b < S is an exact int8 x int8 -> int32 tcgen05.mma, orders are recombined in int64 and
- * scaled to FP64 once.  S = 4 agrees with the FP64 kernel to ~1e-10 relative (tests: 1e-9).
+ * both operands are split into S radix-256 digits (digit 0 unsigned, the rest signed), every digit product of order
+ * a+b < S is an exact int8 x int8 -> int32 tcgen05.mma, orders are recombined in int64 and scaled to FP64 once.
+ * S = 4 (or 5) agrees with the FP64 kernel to ~1e-10 relative (tests: 1e-9).  The Khatri-Rao operand is formed in
+ * integer arithmetic, Z_fix = (xq_i xq_j + rnd(t)) >> 8S from the fixed-point design xq = rint(Xp 2^(8S-e) + dither),
+ * so the resident digit planes (build_z) and the tiles the streaming kernel builds in shared memory (mma_stream) are
+ * the same numbers and both kernels return the same Jint bit for bit.
  *   pyglm_gram_tc_geometry   out[8] = {M pairs, Mpad, Tpad, Npad, neurons per tile, neuron tiles, time chunks,
  *                                      64-byte K blocks per chunk}                                   [host]
  *   pyglm_column_max         cmax[c] = max_t A[t,c] (A >= 0), *neg_flag = 1 if any entry is negative
@@ -88,9 +91,15 @@ int pyglm_weighted_gram(const double* Xp, int ldx, int T, const double* Om, int 
  *                            maximum over the WHOLE recording (all-reduced by the caller) and the rounding dither is
  *                            keyed by the global bin, so the digits do not depend on how the time axis is cut
  *   pyglm_gram_tc_slice_digits  the digit planes of omega for a GIVEN per-neuron scale omax (all-reduced slab maxima)
- *   pyglm_gram_tc_slice_omega  per sweep: omax[n] = max_t Om[t,n] and digit planes Os[S][Npad][Tpad]
+ *   pyglm_gram_tc_slice_omega  per sweep: omax[n] = max_t Om[t,n] and digit planes Os[S][Npad][Tpad] (tiled = 0, for
+ *                            pyglm_gram_tc_mma) or K-block-major Os[S][Tpad/64][Npad][64] (tiled = 1, for mma_stream)
  *   pyglm_gram_tc_mma        Jint[n][pair] = sum_t sum_{a+b<S} 256^(S-1-a-b) Zs[a][pair][t] Os[b][n][t]  (exact int64)
- *   pyglm_gram_tc_finalize   J[n][i][j] = Jint[n][pair] * 2^(ex_i + ex_j + eo_n - 8S - 8), lower triangle        */
+ *   pyglm_gram_tc_finalize   J[n][i][j] = Jint[n][pair] * 2^(ex_i + ex_j + eo_n - 8S - 8), lower triangle
+ *   pyglm_gram_tc_stream_tiles  (i block, j block) of the 8 x 16 pair tiles of the streaming kernel          [host]
+ *   pyglm_gram_tc_quantize   xq[Tpad/32][Dp][32] uint32 fixed-point design (S = 4; Dp = D rounded up to 16; zeroed by
+ *                            the caller) and rw[Tpad] uint64 rounding addends of a time slab; once per dataset
+ *   pyglm_gram_tc_mma_stream the integer GEMM of pyglm_gram_tc_mma with NO resident Z: digit tiles of Z are built in
+ *                            shared memory from xq / rw inside the kernel (S = 4); same Jint                     */
 int pyglm_gram_tc_geometry(int D, int n_valid, long long T, int S, long long* out /*[host]*/);
 int pyglm_column_max(const double* A, int ld, long long T, int ncols, double* cmax, int* neg_flag,
                      pyglm_stream_t stream);
@@ -99,9 +108,10 @@ int pyglm_gram_tc_build_z(const double* Xp, int ldx, long long T, int D, const d
 int pyglm_gram_tc_build_z_slab(const double* Xp, int ldx, long long T, long long t_off, int D, const double* cmax,
                                int S, unsigned char* Zs, long long Mpad, long long Tpad, pyglm_stream_t stream);
 int pyglm_gram_tc_slice_digits(const double* Om, int ldo, long long T, int n_valid, int S, const double* omax,
-                               unsigned char* Os, int Npad, long long Tpad, pyglm_stream_t stream);
+                               unsigned char* Os, int Npad, long long Tpad, int tiled, pyglm_stream_t stream);
 int pyglm_gram_tc_slice_omega(const double* Om, int ldo, long long T, int n_valid, int S, double* omax,
-                              int* neg_flag, unsigned char* Os, int Npad, long long Tpad, pyglm_stream_t stream);
+                              int* neg_flag, unsigned char* Os, int Npad, long long Tpad, int tiled,
+                              pyglm_stream_t stream);
 int pyglm_gram_tc_mma(const unsigned char* Zs, const unsigned char* Os, int D, int n_valid, long long T, int S,
                       long long* Jint, long long ldjint, int max_ctas, pyglm_stream_t stream);
 /* measurement hook: the MMA schedule above without operand loads / result atomics (int8 tensor-pipe peak) */
@@ -109,6 +119,12 @@ int pyglm_gram_tc_mma_probe(const unsigned char* Zs, const unsigned char* Os, in
                             long long* Jint, long long ldjint, pyglm_stream_t stream);
 int pyglm_gram_tc_finalize(const long long* Jint, long long ldjint, const double* cmax, const double* omax,
                            int D, int n_valid, int S, double* J, long long stride_n, int ldj, pyglm_stream_t stream);
+int pyglm_gram_tc_stream_tiles(int D, int* tiles /*[host]*/, int capacity);
+int pyglm_gram_tc_quantize(const double* Xp, int ldx, long long T, long long t_off, int D, const double* cmax,
+                           unsigned int* xq, unsigned long long* rw, long long Tpad, pyglm_stream_t stream);
+int pyglm_gram_tc_mma_stream(const unsigned int* xq, const unsigned long long* rw, const unsigned char* Os, int D,
+                             int n_valid, long long T, int S, const int* tiles /*[device]*/, int n_tiles,
+                             long long* Jint, long long ldjint, int max_ctas, pyglm_stream_t stream);
 
 /* (4) spike-and-slab update of (a, W, b).  pyglm/regression.py:265-340 (_collapsed_resample_a,
  * _marginal_likelihood, _resample_W) with pybasicbayes' sample_discrete_from_log / sample_gaussian. */

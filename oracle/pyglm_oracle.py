@@ -561,9 +561,9 @@ def tc_exponent(cmax):
     return 0 if not cmax > 0 else math.frexp(cmax * 1.02)[1]
 
 
-def tc_digits(scaled, S):
-    """S radix-256 digits of rint(scaled): digit 0 (most significant) unsigned, the others signed round-to-nearest."""
-    v = np.rint(scaled).astype(np.int64)
+def tc_digits_int(v, S):
+    """S radix-256 digits of the integer array v >= 0: digit 0 (most significant) unsigned, the others signed."""
+    v = np.asarray(v, dtype=np.int64).copy()
     out = []
     for _ in range(S - 1):
         lo = ((v + 128) & 255) - 128
@@ -573,8 +573,13 @@ def tc_digits(scaled, S):
     return out[::-1]
 
 
+def tc_digits(scaled, S):
+    """S radix-256 digits of rint(scaled) (the omega operand)."""
+    return tc_digits_int(np.rint(scaled).astype(np.int64), S)
+
+
 def tc_dither(p, t):
-    """Index-keyed dither in (-1/2, 1/2) added before rounding Z to its fixed-point grid (gram_tc.cu: tc_dither)."""
+    """Index-keyed dither in (-1/2, 1/2) added before rounding X~ to its fixed-point grid (gram_tc.cu: tc_dither)."""
     with np.errstate(over="ignore"):
         h = np.asarray(p, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) \
             + np.asarray(t, dtype=np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
@@ -586,33 +591,69 @@ def tc_dither(p, t):
     return ((h >> np.uint64(40)).astype(np.float64) + 0.5) * 2.0 ** -24 - 0.5
 
 
-def tc_z_digits(Xt, i, j, ex, S):
-    """Digits of Z[:, (i,j)] = Xt[:, i] Xt[:, j] as gram_tc.cu stores them (pair index i(i+1)/2 + j)."""
+def tc_rword(t):
+    """Per-bin dither word of the product rounding (gram_tc.cu: tc_rword = lowbias32 of the global bin index)."""
+    t = np.asarray(t, dtype=np.uint64)
+    m = np.uint64(0xFFFFFFFF)
+    x = ((t & m) ^ (((t >> np.uint64(32)) * np.uint64(0x9E3779B9)) & m)) & m
+    x = ((x ^ (x >> np.uint64(16))) * np.uint64(0x7FEB352D)) & m
+    x = ((x ^ (x >> np.uint64(15))) * np.uint64(0x846CA68B)) & m
+    return x ^ (x >> np.uint64(16))
+
+
+def tc_xq(Xt, i, ex, S, t_off=0):
+    """Fixed-point column i of the design: rint(x 2^(8S - e_i) + dither(i, global bin)) as Python-int-safe uint64."""
     T = Xt.shape[0]
-    p = i * (i + 1) // 2 + j
-    scaled = Xt[:, j] * Xt[:, i] * 2.0 ** (8 * S - ex[i] - ex[j])
-    return tc_digits(scaled + tc_dither(np.full(T, p, dtype=np.uint64), np.arange(T, dtype=np.uint64)), S)
+    t = np.arange(T, dtype=np.uint64) + np.uint64(t_off)
+    v = np.rint(Xt[:, i] * 2.0 ** (8 * S - ex[i]) + tc_dither(np.full(T, i, dtype=np.uint64), t))
+    return v.astype(np.int64).astype(np.uint64)
 
 
-def tc_gram_reference(Xt, om, S):
+def tc_z_fix(Xt, i, j, ex, S, t_off=0):
+    """Z_fix[t] = (xq_i xq_j + rnd(t)) >> 8S as gram_tc.cu forms it (integer arithmetic; pair index i(i+1)/2 + j)."""
+    T = Xt.shape[0]
+    rw = tc_rword(np.arange(T, dtype=np.uint64) + np.uint64(t_off))
+    xi, xj = tc_xq(Xt, i, ex, S, t_off), tc_xq(Xt, j, ex, S, t_off)
+    if S == 4:
+        return ((xi * xj + rw) >> np.uint64(32)).astype(np.int64)           # < 2^64: exact in uint64
+    assert S == 5
+    add = (rw << np.uint64(8)) | (rw >> np.uint64(24))
+    return np.array([(int(a) * int(b) + int(c)) >> 40 for a, b, c in zip(xi, xj, add)], dtype=np.int64)
+
+
+def tc_z_digits(Xt, i, j, ex, S, t_off=0):
+    """Digits of Z[:, (i,j)] = Xt[:, i] Xt[:, j] as gram_tc.cu stores / builds them."""
+    return tc_digits_int(tc_z_fix(Xt, i, j, ex, S, t_off), S)
+
+
+def tc_gram_reference(Xt, om, S, t_off=0, ex=None, eo=None):
     """Xt (T, D) = [X, 1] >= 0, om (T, n) > 0.  Returns (Jint (n, D(D+1)/2) int64 exact digit sums,
-    J (n, D, D) float64 lower triangle) as gram_tc.cu computes them."""
+    J (n, D, D) float64 lower triangle) as gram_tc.cu computes them.  ex / eo: scale exponents when they come from a
+    longer recording than Xt (time slabs).  The digit dot products run as float64 matrix products: every partial sum
+    is an integer below 2^53, hence exact."""
     T, D = Xt.shape
     n = om.shape[1]
-    ex = [tc_exponent(c) for c in Xt.max(0)]
-    eo = [tc_exponent(c) for c in om.max(0)]
-    od = [tc_digits(om[:, c] * 2.0 ** (8 * S - eo[c]), S) for c in range(n)]
+    assert T * 4 * 255 * 255 < 2 ** 53
+    ex = [tc_exponent(c) for c in Xt.max(0)] if ex is None else ex
+    eo = [tc_exponent(c) for c in om.max(0)] if eo is None else eo
+    od = [np.stack([tc_digits(om[:, c] * 2.0 ** (8 * S - eo[c]), S)[b] for c in range(n)], axis=1).astype(np.float64)
+          for b in range(S)]                                              # od[b]: (T, n)
+    xq = np.stack([tc_xq(Xt, i, ex, S, t_off) for i in range(D)], axis=1)  # (T, D) uint64
+    rw = tc_rword(np.arange(T, dtype=np.uint64) + np.uint64(t_off))
     Jint = np.zeros((n, D * (D + 1) // 2), dtype=np.int64)
     J = np.zeros((n, D, D))
     for i in range(D):
-        for j in range(i + 1):
-            p = i * (i + 1) // 2 + j
-            zd = tc_z_digits(Xt, i, j, ex, S)
-            for c in range(n):
-                tot = 0
-                for a in range(S):
-                    for b in range(S - a):
-                        tot += int(np.dot(zd[a], od[c][b])) << (8 * (S - 1 - a - b))
-                Jint[c, p] = tot
-                J[c, i, j] = float(tot) * 2.0 ** (ex[i] + ex[j] + eo[c] - 8 * S - 8)
+        if S == 4:
+            z = ((xq[:, i:i + 1] * xq[:, :i + 1] + rw[:, None]) >> np.uint64(32)).astype(np.int64)   # (T, i+1)
+        else:
+            z = np.stack([tc_z_fix(Xt, i, j, ex, S, t_off) for j in range(i + 1)], axis=1)
+        zd = [d.astype(np.float64) for d in tc_digits_int(z, S)]          # zd[a]: (T, i+1)
+        tot = np.zeros((i + 1, n), dtype=np.int64)
+        for a in range(S):
+            for b in range(S - a):
+                tot += (zd[a].T @ od[b]).astype(np.int64) << (8 * (S - 1 - a - b))
+        p0 = i * (i + 1) // 2
+        Jint[:, p0:p0 + i + 1] = tot.T
+        for c in range(n):
+            J[c, i, :i + 1] = tot[:, c].astype(np.float64) * 2.0 ** (np.array(ex[:i + 1]) + ex[i] + eo[c] - 8 * S - 8)
     return Jint, J

@@ -36,11 +36,14 @@ SIGNATURES = {
     "pyglm_column_max": (c_int, [ptr, c_int, c_ll, c_int, ptr, ptr, ptr]),
     "pyglm_gram_tc_build_z": (c_int, [ptr, c_int, c_ll, c_int, ptr, c_int, ptr, c_ll, c_ll, ptr]),
     "pyglm_gram_tc_build_z_slab": (c_int, [ptr, c_int, c_ll, c_ll, c_int, ptr, c_int, ptr, c_ll, c_ll, ptr]),
-    "pyglm_gram_tc_slice_digits": (c_int, [ptr, c_int, c_ll, c_int, c_int, ptr, ptr, c_int, c_ll, ptr]),
-    "pyglm_gram_tc_slice_omega": (c_int, [ptr, c_int, c_ll, c_int, c_int, ptr, ptr, ptr, c_int, c_ll, ptr]),
+    "pyglm_gram_tc_slice_digits": (c_int, [ptr, c_int, c_ll, c_int, c_int, ptr, ptr, c_int, c_ll, c_int, ptr]),
+    "pyglm_gram_tc_slice_omega": (c_int, [ptr, c_int, c_ll, c_int, c_int, ptr, ptr, ptr, c_int, c_ll, c_int, ptr]),
     "pyglm_gram_tc_mma": (c_int, [ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_ll, c_int, ptr]),
     "pyglm_gram_tc_mma_probe": (c_int, [ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_ll, ptr]),
     "pyglm_gram_tc_finalize": (c_int, [ptr, c_ll, ptr, ptr, c_int, c_int, c_int, ptr, c_ll, c_int, ptr]),
+    "pyglm_gram_tc_stream_tiles": (c_int, [c_int, ptr, c_int]),
+    "pyglm_gram_tc_quantize": (c_int, [ptr, c_int, c_ll, c_ll, c_int, ptr, ptr, ptr, c_ll, ptr]),
+    "pyglm_gram_tc_mma_stream": (c_int, [ptr, ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_int, ptr, c_ll, c_int, ptr]),
     "pyglm_generate": (c_int, [ptr, ptr, ptr, c_int, c_int, c_int, c_ll, c_ull, c_uint, ctypes.c_double, ptr, c_int, ptr,
                                ptr, ptr]),
     "pyglm_spike_slab_workspace_doubles": (size_t, [c_int, c_int, c_int]),

@@ -7,8 +7,13 @@
 // Both operands are written as S radix-256 digits of a fixed-point number with a power-of-two scale per row,
 //     Z[t,p]     ~ 2^(ex_i+ex_j-8S) * sum_s 256^(S-1-s) zs[s][p][t]       (scale: product of column bounds of X~)
 //     omega[t,n] ~ 2^(eo_n-8S)      * sum_s 256^(S-1-s) os[s][n][t]       (scale: column maximum of omega)
-// digit 0 unsigned in [0,255] (all operands are >= 0 on this path), digits 1.. signed round-to-nearest in
-// [-128,127], so the dropped tail is zero-mean (Z is rounded with an index-keyed dither, see tc_dither).  Every digit product zs[a] * os[b] with a+b <= S-1 is one
+// digit 0 unsigned in [0,255] (all operands are >= 0 on this path), digits 1.. signed in [-128,127].  Z is formed in
+// INTEGER arithmetic from the fixed-point design xq[i][t] = rint(X~[t,i] 2^(8S-ex_i) + dither(i,t)):
+//     Z_fix[(i,j)][t] = (xq_i xq_j + rnd(t)) >> 8S             rnd = bin-keyed dither of the dropped low half
+// so a digit tile is a pure function of two rows of xq -- cheap enough to be rebuilt inside the GEMM kernel from the
+// (D x T) fixed-point design instead of being streamed from 4 M T bytes of HBM (gram_tcs_kernel below), and identical
+// bit for bit whether it is built there, built once into resident planes (zslice_kernel), or by the numpy emulation
+// in the tests.  Every digit product zs[a] * os[b] with a+b <= S-1 is one
 // tcgen05.mma into the int32 accumulator of "order" g = a+b; sums of at most 16384 time bins stay below 2^31, so
 // each accumulator is EXACT, and orders are recombined as int64 (sum_g acc_g << 8(S-1-g)), added across time chunks
 // with integer atomics (order-independent => bitwise deterministic) and scaled to FP64 once at the end.
@@ -45,6 +50,15 @@ __host__ __device__ inline int tc_exponent(double cmax) {
     frexp(cmax * 1.02, &e);
     return e;
 }
+
+// 32-bit mixer (lowbias32) behind the product dither
+__host__ __device__ inline uint32_t tc_hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+// per-time-bin dither word of the product rounding.  The same word serves every pair of a bin: what matters for the
+// sum over time of ONE pair is that its rounding errors are independent from bin to bin.
+__host__ __device__ inline uint32_t tc_rword(unsigned long long t_global) { return tc_hash32((uint32_t)t_global ^ (uint32_t)(t_global >> 32) * 0x9E3779B9u); }
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -169,6 +183,9 @@ struct TcItems {
     int multicast;          // 1: clusters of two CTAs share each Z tile through TMA multicast (needs n_ntiles == 2)
     int n_ctas;             // CTAs taking part in the item schedule (a multiple of n_ntiles)
     int probe;              // 1: issue-rate probe -- no operand loads, no result atomics (tensor-pipe peak measurement)
+    const int* tiles;       // streaming kernel: (i block, j block) of every 8 x 16 pair tile, n_mtiles entries (device)
+    int D;                  // streaming kernel: columns of the design (pairs (i, j), j <= i < D)
+    int Dp;                 // streaming kernel: rows per 32-bin block of the tiled fixed-point design (D rounded up to 16)
 };
 
 // Item schedule.  CTAs are grouped n_ntiles at a time; in round k group q works on (pair tile, time chunk) number
@@ -363,6 +380,520 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------ streaming variant
+// The same integer GEMM with the Z digit tiles BUILT IN SHARED MEMORY instead of streamed from resident planes:
+// nothing of size pairs x T exists in HBM (cfg4 / cfg5: 228 / 250 GB per rank do not fit; cfg3: 32 GB and a 37 ms
+// build per data set disappear, and neuron-sharded ranks no longer stream all of Z for a fraction of the neurons).
+// A pair tile is 8 rows i x 16 rows j of the design (TMEM lane r <-> pair (i0 + r/16, j0 + r%16)), so one K block of
+// 64 time bins needs only 24 rows of the fixed-point design xq (6 KB through TMA, SWIZZLE_128B) plus the 64 dither
+// words -- against 32 KB of Z digits in the resident kernel: the L2 -> SM traffic per MMA drops, which is what bounds
+// the resident kernel (ncu: IMMA pipe 78 %, L2 near its throughput cap).
+//   warp 0     TMA producer: S omega digit tiles, 6 boxes of xq (i rows, j rows; two 32-bin halves), 64 dither words
+//   warp 1     MMA issuer (unchanged)
+//   warps 2-5  epilogue (unchanged but for the lane -> pair map)
+//   warps 6-13 builders: two threads per pair row r: per K block 2 x 32 products xq_i xq_j + rnd (one IMAD.WIDE each, the
+//              signed-digit offset 0x00808080 riding in the addend's high word), 4 x 4 byte transposes (PRMT), and 16
+//              STS.128 into the four SWIZZLE_64B digit tiles, then fence.proxy.async + arrive on the stage's Z barrier
+constexpr int TS_TI = 8, TS_TJ = 16;
+constexpr int TS_STAGES = 3;
+constexpr int TS_BUILD_WARPS = 8;           // two builder threads per pair row: one per 32-bin half of a K block
+constexpr int TS_THREADS = 192 + 32 * TS_BUILD_WARPS;
+constexpr int TS_XQ_BYTES = 6 * 1024;       // [half][i rows | j rows 0-7 | j rows 8-15][8 rows x 128 B]
+constexpr int TS_RW_BYTES = 512;            // 64 addends {dither word, 0x00808080}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// (xi * xj + {rnd, 0x00808080}) >> 32: byte 3 = digit 0 (unsigned), bytes 2..0 = digits 1..3 + 128 (the xor with 0x80
+// that makes them signed is applied to four bins at once after the byte transpose).  The addend arrives from shared
+// memory as an aligned register pair, so this is one IMAD.WIDE.
+__device__ __forceinline__ uint32_t ts_digits4(uint32_t xi, uint32_t xj, unsigned long long addend) {
+    return (uint32_t)(((unsigned long long)xi * xj + addend) >> 32);
+}
+__device__ __forceinline__ void lds128_2x64(uint32_t addr, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+
+template <int S>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+gram_tcs_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapO,
+                const unsigned long long* __restrict__ rw, long long* __restrict__ Jint, const TcItems it) {
+    static_assert(S == 4, "the streaming builder packs one 32-bit fixed-point product into four digits");
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    constexpr int A_SLICE = TC_BM * TC_BK;
+    const int B_SLICE = it.nt * TC_BK;
+    constexpr int O_OFF = S * A_SLICE;
+    const int XQ_OFF = O_OFF + S * tc_nt_max(S) * TC_BK;
+    const int RW_OFF = XQ_OFF + TS_XQ_BYTES;
+    const int STAGE = (RW_OFF + TS_RW_BYTES + 1023) & ~1023;
+    const uint32_t stage_tx = (uint32_t)(S * B_SLICE + TS_XQ_BYTES + TS_RW_BYTES);
+    __shared__ __align__(8) uint64_t bars[3 * TS_STAGES + 2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t sbase = (smem_u32(tc_smem) + 1023u) & ~1023u;
+    const uint32_t fin0 = smem_u32(&bars[0]), fz0 = smem_u32(&bars[TS_STAGES]), empty0 = smem_u32(&bars[2 * TS_STAGES]);
+    const uint32_t tfull = smem_u32(&bars[3 * TS_STAGES]), tempty = smem_u32(&bars[3 * TS_STAGES + 1]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS_STAGES; ++s) {
+            mbar_init(fin0 + 8 * s, 1);          // TMA producer's expect_tx arrival
+            mbar_init(fz0 + 8 * s, TS_BUILD_WARPS);   // one arrival per builder warp
+            mbar_init(empty0 + 8 * s, 1);        // tcgen05.commit
+        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int acc_cols = 512 / S / 16 * 16;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int kb0 = wk.chunk * it.blocks_per_chunk;
+            const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+            const int i0 = it.tiles[2 * wk.mtile] * TS_TI, j0 = it.tiles[2 * wk.mtile + 1] * TS_TJ;
+            const int rowo = wk.ntile * it.nt;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = fin0 + 8 * stage;
+                    mbar_expect_tx(fb, stage_tx);
+                    const uint32_t st = sbase + stage * STAGE;
+#pragma unroll
+                    for (int s = 0; s < S; ++s)
+                        tma_load_2d(st + O_OFF + s * B_SLICE, &mapO, 0, (s * it.n_blocks + kb) * it.Npad + rowo, fb);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int y0 = (2 * kb + h) * it.Dp;       // rows of this 32-bin block in the tiled design
+                        tma_load_2d(st + XQ_OFF + (h * 3 + 0) * 1024, &mapX, 0, y0 + i0, fb);
+                        tma_load_2d(st + XQ_OFF + (h * 3 + 1) * 1024, &mapX, 0, y0 + j0, fb);
+                        tma_load_2d(st + XQ_OFF + (h * 3 + 2) * 1024, &mapX, 0, y0 + j0 + 8, fb);
+                    }
+                    bulk_load(st + RW_OFF, rw + (long long)kb * TC_BK, TS_RW_BYTES, fb);
+                }
+                __syncwarp();
+                if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        int stage = 0;
+        uint32_t phase = 0, tphase = 0;
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int n_mma = tc_tile_n(it, wk.ntile);
+            const uint32_t id_uu = tc_idesc(0, 0, n_mma), id_us = tc_idesc(0, 1, n_mma);
+            const uint32_t id_su = tc_idesc(1, 0, n_mma), id_ss = tc_idesc(1, 1, n_mma);
+            const int kb0 = wk.chunk * it.blocks_per_chunk;
+            const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+            mbar_wait(tempty, tphase ^ 1);
+            tc_fence_after();
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(fin0 + 8 * stage, phase);          // omega tiles have landed (TMA)
+                mbar_wait(fz0 + 8 * stage, phase);           // Z tiles have been built (generic proxy, fenced)
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = sbase + stage * STAGE;
+                    const uint64_t da = tc_smem_desc(sa), db = tc_smem_desc(sa + O_OFF);
+                    const uint32_t first = (kb > kb0) ? 1u : 0u;
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {
+#pragma unroll
+                        for (int a = 0; a < S; ++a) {
+#pragma unroll
+                            for (int b = 0; b + a < S; ++b) {
+                                const uint64_t adesc = da + (uint64_t)((a * A_SLICE + ks * TC_UK) >> 4);
+                                const uint64_t bdesc = db + (uint64_t)((b * B_SLICE + ks * TC_UK) >> 4);
+                                const uint32_t acc = (ks > 0 || a > 0) ? 1u : first;
+                                const uint32_t idesc = (a > 0) ? ((b > 0) ? id_ss : id_su) : ((b > 0) ? id_us : id_uu);
+                                tc_mma_i8(tmem + (uint32_t)((a + b) * acc_cols), adesc, bdesc, idesc, acc);
+                            }
+                        }
+                    }
+                    tc_commit(empty0 + 8 * stage);
+                }
+                __syncwarp();
+                if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) tc_commit(tfull);
+            __syncwarp();
+            tphase ^= 1;
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;
+        uint32_t tphase = 0;
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int ntile = wk.ntile;
+            const int n_mma = tc_tile_n(it, ntile);
+            const int r = quarter * 32 + lane;
+            const int i = it.tiles[2 * wk.mtile] * TS_TI + (r >> 4), j = it.tiles[2 * wk.mtile + 1] * TS_TJ + (r & 15);
+            const bool row_ok = (i < it.D) && (j <= i);
+            const long long row = (long long)i * (i + 1) / 2 + j;
+            mbar_wait(tfull, tphase);
+            tphase ^= 1;
+            tc_fence_after();
+            const int n0 = ntile * it.nt;
+            for (int c0 = 0; c0 < n_mma; c0 += 16) {
+                int acc[S][16];
+#pragma unroll
+                for (int g = 0; g < S; ++g)
+                    tc_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * acc_cols + c0), acc[g]);
+                tc_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        long long v = 0;
+#pragma unroll
+                        for (int g = 0; g < S; ++g) v += (long long)acc[g][c] * (1LL << (8 * (S - 1 - g)));
+                        const int n = n0 + c0 + c;
+                        if (n < it.n_valid && v != 0)
+                            atomicAdd(reinterpret_cast<unsigned long long*>(Jint + (long long)n * it.ldj + row),
+                                      (unsigned long long)v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
+    } else {
+        // ------------------------------------------------------------------ builders (warps 6..13): thread <-> (pair row r,
+        // 32-bin half of the K block); a single warp per scheduler would leave the build latency-bound
+        const int r = ((int)threadIdx.x - 192) & 127;
+        const int hsel = ((int)threadIdx.x - 192) >> 7;
+        const int il = r >> 4, jl = r & 15;
+        const uint32_t xi_off = (uint32_t)(il * 128);                                   // in box 0 of a half
+        const uint32_t xj_off = (uint32_t)((1 + (jl >> 3)) * 1024 + (jl & 7) * 128);   // in box 1 or 2
+        const uint32_t xi_sw = (uint32_t)(il & 7), xj_sw = (uint32_t)(jl & 7);
+        const uint32_t z_row = (uint32_t)(r * TC_BK), z_sw = (uint32_t)((r >> 1) & 3);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int kb0 = wk.chunk * it.blocks_per_chunk;
+            const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(fin0 + 8 * stage, phase);
+                const uint32_t st = sbase + stage * STAGE;
+#pragma unroll
+                for (int zz = 0; zz < 2; ++zz) {                 // 16 time bins -> one 16-byte chunk per digit tile
+                    const int zc = 2 * hsel + zz;
+                    const uint32_t half = st + XQ_OFF + (uint32_t)(hsel * 3 * 1024);
+                    uint32_t pl[S][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t c = (uint32_t)(zz * 4 + q);
+                        const uint4 a = lds128(half + xi_off + ((c ^ xi_sw) << 4));
+                        const uint4 b = lds128(half + xj_off + ((c ^ xj_sw) << 4));
+                        unsigned long long d0, d1, d2, d3;
+                        lds128_2x64(st + RW_OFF + (uint32_t)((zc * 4 + q) << 5), d0, d1);
+                        lds128_2x64(st + RW_OFF + (uint32_t)((zc * 4 + q) << 5) + 16u, d2, d3);
+                        const uint32_t w0 = ts_digits4(a.x, b.x, d0), w1 = ts_digits4(a.y, b.y, d1);
+                        const uint32_t w2 = ts_digits4(a.z, b.z, d2), w3 = ts_digits4(a.w, b.w, d3);
+                        // 4 x 4 byte transpose: pl[s] = digit s of the four bins (byte k = bin k)
+                        const uint32_t lo01 = __byte_perm(w0, w1, 0x5140), hi01 = __byte_perm(w0, w1, 0x7362);
+                        const uint32_t lo23 = __byte_perm(w2, w3, 0x5140), hi23 = __byte_perm(w2, w3, 0x7362);
+                        pl[3][q] = __byte_perm(lo01, lo23, 0x5410) ^ 0x80808080u;
+                        pl[2][q] = __byte_perm(lo01, lo23, 0x7632) ^ 0x80808080u;
+                        pl[1][q] = __byte_perm(hi01, hi23, 0x5410) ^ 0x80808080u;
+                        pl[0][q] = __byte_perm(hi01, hi23, 0x7632);
+                    }
+                    const uint32_t zaddr = st + z_row + (((uint32_t)zc ^ z_sw) << 4);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) sts128(zaddr + s * A_SLICE, pl[s][0], pl[s][1], pl[s][2], pl[s][3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tcgen05 reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(fz0 + 8 * stage);
+                if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ streaming, Z tiles in TMEM
+// gram_tcs_kernel measured 1.16 us per 64-bin K block at cfg4's slab against 0.57 us of tensor time: it is bound by
+// SHARED-MEMORY BANDWIDTH, like the resident kernel (per K block the 20 MMAs read 20 x (4 KB of A + 3.5 KB of B), TMA
+// writes 38 KB and the builders move ~70 KB: 260 KB at 128 B/cycle = 2050 cycles; the resident kernel's 194 KB = 1520
+// cycles is its measured 0.89 us).  So here the built Z tile never touches shared memory: the builders write their digit
+// words with tcgen05.st into a double-buffered A operand in TENSOR MEMORY (TMEM lane r = pair row r, 8 columns = 32 bins
+// of one digit), and the MMAs take A from TMEM (tcgen05.mma [d], [a], b-desc).  The S accumulators are packed at a pitch
+// of nt columns so that S * nt + 64 <= 512 (nt <= 112).  What is left in shared memory per K block is the omega tile
+// (TMA write + 20 B-operand reads) and the 7 KB of fixed-point design the builders read: ~145 KB = the tensor time.
+//   K granularity: one MMA K step (32 bins).  Builder warps 6-9 fill A buffer 0 with bins 0-31 of every 64-bin block,
+//   warps 10-13 fill buffer 1 with bins 32-63; warp w owns TMEM lanes 32 (w % 4) .. + 31 (the tcgen05.st lane rule).
+constexpr int TM_STAGES = 5;
+constexpr int TM_NT_MAX = 112;
+
+__device__ __forceinline__ void tc_mma_i8_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int S>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+gram_tcm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapO,
+                const unsigned long long* __restrict__ rw, long long* __restrict__ Jint, const TcItems it) {
+    static_assert(S == 4, "the streaming builder packs one 32-bit fixed-point product into four digits");
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    const int B_SLICE = it.nt * TC_BK;
+    constexpr int XQ_OFF = S * TM_NT_MAX * TC_BK;
+    constexpr int RW_OFF = XQ_OFF + TS_XQ_BYTES;
+    constexpr int STAGE = (RW_OFF + TS_RW_BYTES + 1023) & ~1023;
+    const uint32_t stage_tx = (uint32_t)(S * B_SLICE + TS_XQ_BYTES + TS_RW_BYTES);
+    __shared__ __align__(8) uint64_t bars[2 * TM_STAGES + 6];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t sbase = (smem_u32(tc_smem) + 1023u) & ~1023u;
+    const uint32_t fin0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TM_STAGES]);
+    const uint32_t afull0 = smem_u32(&bars[2 * TM_STAGES]), aempty0 = smem_u32(&bars[2 * TM_STAGES + 2]);
+    const uint32_t tfull = smem_u32(&bars[2 * TM_STAGES + 4]), tempty = smem_u32(&bars[2 * TM_STAGES + 5]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TM_STAGES; ++s) { mbar_init(fin0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int h = 0; h < 2; ++h) { mbar_init(afull0 + 8 * h, TS_BUILD_WARPS / 2); mbar_init(aempty0 + 8 * h, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int acc_cols = it.nt;                                   // accumulator of order g at columns [g nt, (g+1) nt)
+    const uint32_t a_col = (uint32_t)(S * it.nt);                 // A operand: buffer h, digit a at a_col + 32 h + 8 a
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int kb0 = wk.chunk * it.blocks_per_chunk;
+            const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+            const int i0 = it.tiles[2 * wk.mtile] * TS_TI, j0 = it.tiles[2 * wk.mtile + 1] * TS_TJ;
+            const int rowo = wk.ntile * it.nt;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = fin0 + 8 * stage;
+                    mbar_expect_tx(fb, stage_tx);
+                    const uint32_t st = sbase + stage * STAGE;
+#pragma unroll
+                    for (int s = 0; s < S; ++s)
+                        tma_load_2d(st + s * B_SLICE, &mapO, 0, (s * it.n_blocks + kb) * it.Npad + rowo, fb);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int y0 = (2 * kb + h) * it.Dp;       // rows of this 32-bin block in the tiled design
+                        tma_load_2d(st + XQ_OFF + (h * 3 + 0) * 1024, &mapX, 0, y0 + i0, fb);
+                        tma_load_2d(st + XQ_OFF + (h * 3 + 1) * 1024, &mapX, 0, y0 + j0, fb);
+                        tma_load_2d(st + XQ_OFF + (h * 3 + 2) * 1024, &mapX, 0, y0 + j0 + 8, fb);
+                    }
+                    bulk_load(st + RW_OFF, rw + (long long)kb * TC_BK, TS_RW_BYTES, fb);
+                }
+                __syncwarp();
+                if (++stage == TM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        int stage = 0;
+        uint32_t phase = 0, tphase = 0, aphase = 0;
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int n_mma = tc_tile_n(it, wk.ntile);
+            const uint32_t id_uu = tc_idesc(0, 0, n_mma), id_us = tc_idesc(0, 1, n_mma);
+            const uint32_t id_su = tc_idesc(1, 0, n_mma), id_ss = tc_idesc(1, 1, n_mma);
+            const int kb0 = wk.chunk * it.blocks_per_chunk;
+            const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+            mbar_wait(tempty, tphase ^ 1);
+            tc_fence_after();
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(fin0 + 8 * stage, phase);          // omega tiles have landed
+                const uint32_t sa = sbase + stage * STAGE;
+                const uint64_t db = tc_smem_desc(sa);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(afull0 + 8 * h, aphase);       // the builders have stored this half's Z digits into TMEM
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t first = (kb > kb0 || h > 0) ? 1u : 0u;
+#pragma unroll
+                        for (int a = 0; a < S; ++a) {
+#pragma unroll
+                            for (int b = 0; b + a < S; ++b) {
+                                const uint64_t bdesc = db + (uint64_t)((b * B_SLICE + h * TC_UK) >> 4);
+                                const uint32_t acc = (a > 0) ? 1u : first;
+                                const uint32_t idesc = (a > 0) ? ((b > 0) ? id_ss : id_su) : ((b > 0) ? id_us : id_uu);
+                                tc_mma_i8_ta(tmem + (uint32_t)((a + b) * acc_cols), tmem + a_col + (uint32_t)(32 * h + 8 * a),
+                                             bdesc, idesc, acc);
+                            }
+                        }
+                        tc_commit(aempty0 + 8 * h);          // A buffer h may be overwritten once these MMAs have read it
+                        if (h == 1) tc_commit(empty0 + 8 * stage);
+                    }
+                    __syncwarp();
+                }
+                aphase ^= 1;
+                if (++stage == TM_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) tc_commit(tfull);
+            __syncwarp();
+            tphase ^= 1;
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;
+        uint32_t tphase = 0;
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int ntile = wk.ntile;
+            const int n_mma = tc_tile_n(it, ntile);
+            const int r = quarter * 32 + lane;
+            const int i = it.tiles[2 * wk.mtile] * TS_TI + (r >> 4), j = it.tiles[2 * wk.mtile + 1] * TS_TJ + (r & 15);
+            const bool row_ok = (i < it.D) && (j <= i);
+            const long long row = (long long)i * (i + 1) / 2 + j;
+            mbar_wait(tfull, tphase);
+            tphase ^= 1;
+            tc_fence_after();
+            const int n0 = ntile * it.nt;
+            for (int c0 = 0; c0 < n_mma; c0 += 16) {
+                int acc[S][16];
+#pragma unroll
+                for (int g = 0; g < S; ++g)
+                    tc_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * acc_cols + c0), acc[g]);
+                tc_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        long long v = 0;
+#pragma unroll
+                        for (int g = 0; g < S; ++g) v += (long long)acc[g][c] * (1LL << (8 * (S - 1 - g)));
+                        const int n = n0 + c0 + c;
+                        if (n < it.n_valid && v != 0)
+                            atomicAdd(reinterpret_cast<unsigned long long*>(Jint + (long long)n * it.ldj + row),
+                                      (unsigned long long)v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
+    } else {
+        // ------------------------------------------------------------------ builders (warps 6..13)
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may write
+        const int hsel = (warp - 6) >> 2;                      // 32-bin half of every K block = A buffer index
+        const int r = quarter * 32 + lane;                     // pair row = TMEM lane
+        const int il = r >> 4, jl = r & 15;
+        const uint32_t xi_off = (uint32_t)(il * 128);
+        const uint32_t xj_off = (uint32_t)((1 + (jl >> 3)) * 1024 + (jl & 7) * 128);
+        const uint32_t xi_sw = (uint32_t)(il & 7), xj_sw = (uint32_t)(jl & 7);
+        const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + a_col + (uint32_t)(32 * hsel);
+        int stage = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int round = 0;; ++round) {
+            const TcWork wk = tc_work(it, round);
+            if (!wk.valid) break;
+            const int kb0 = wk.chunk * it.blocks_per_chunk;
+            const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(fin0 + 8 * stage, phase);
+                const uint32_t st = sbase + stage * STAGE;
+                const uint32_t half = st + XQ_OFF + (uint32_t)(hsel * 3 * 1024);
+                uint32_t pl[S][8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {                    // 4 bins per step: one 32-bit column per digit
+                    const uint4 a = lds128(half + xi_off + (((uint32_t)c ^ xi_sw) << 4));
+                    const uint4 b = lds128(half + xj_off + (((uint32_t)c ^ xj_sw) << 4));
+                    unsigned long long d0, d1, d2, d3;
+                    lds128_2x64(st + RW_OFF + (uint32_t)((hsel * 8 + c) << 5), d0, d1);
+                    lds128_2x64(st + RW_OFF + (uint32_t)((hsel * 8 + c) << 5) + 16u, d2, d3);
+                    const uint32_t w0 = ts_digits4(a.x, b.x, d0), w1 = ts_digits4(a.y, b.y, d1);
+                    const uint32_t w2 = ts_digits4(a.z, b.z, d2), w3 = ts_digits4(a.w, b.w, d3);
+                    const uint32_t lo01 = __byte_perm(w0, w1, 0x5140), hi01 = __byte_perm(w0, w1, 0x7362);
+                    const uint32_t lo23 = __byte_perm(w2, w3, 0x5140), hi23 = __byte_perm(w2, w3, 0x7362);
+                    pl[3][c] = __byte_perm(lo01, lo23, 0x5410) ^ 0x80808080u;
+                    pl[2][c] = __byte_perm(lo01, lo23, 0x7632) ^ 0x80808080u;
+                    pl[1][c] = __byte_perm(hi01, hi23, 0x5410) ^ 0x80808080u;
+                    pl[0][c] = __byte_perm(hi01, hi23, 0x7632);
+                }
+                mbar_wait(aempty0 + 8 * hsel, aphase ^ 1);       // the MMAs of the previous K block have read buffer hsel
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < S; ++s) tc_st8(ta + (uint32_t)(8 * s), pl[s]);
+                tc_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull0 + 8 * hsel);
+                aphase ^= 1;
+                if (++stage == TM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ operand preparation
 // column maxima of a (T x ld) row-major matrix of non-negative entries, as IEEE bit patterns (monotone for x >= 0);
 // *neg is set when a negative entry is seen.  cmax must be zeroed by the caller.
@@ -394,10 +925,9 @@ __host__ __device__ inline double tc_dither(unsigned long long p, unsigned long 
     return ((double)(h >> 40) + 0.5) * (1.0 / 16777216.0) - 0.5;
 }
 
-// S radix-256 digits of round(v): digit 0 (most significant) in [0,255], the others signed in [-128,127]
+// S radix-256 digits of an integer v >= 0: digit 0 (most significant) in [0,255], the others signed in [-128,127]
 template <int S>
-__device__ __forceinline__ void tc_digits(double scaled, unsigned (&d)[S]) {
-    long long v = __double2ll_rn(scaled);
+__device__ __forceinline__ void tc_digits_int(long long v, unsigned (&d)[S]) {
 #pragma unroll
     for (int s = S - 1; s >= 1; --s) {
         const long long lo = ((v + 128) & 255) - 128;
@@ -405,6 +935,23 @@ __device__ __forceinline__ void tc_digits(double scaled, unsigned (&d)[S]) {
         v = (v - lo) >> 8;
     }
     d[0] = (unsigned)(v & 255);
+}
+// S radix-256 digits of round(scaled) (omega)
+template <int S>
+__device__ __forceinline__ void tc_digits(double scaled, unsigned (&d)[S]) {
+    tc_digits_int<S>(__double2ll_rn(scaled), d);
+}
+// fixed-point design entry: rint(x 2^(8S - e) + dither(column, global bin))  (< 2^(8S) / 1.02)
+template <int S>
+__device__ __forceinline__ unsigned long long tc_xq(double x, int e, int col, unsigned long long t_global) {
+    return (unsigned long long)__double2ll_rn(x * ldexp(1.0, 8 * S - e) + tc_dither((unsigned long long)col, t_global));
+}
+// Z_fix = (xq_i xq_j + rnd) >> 8S with rnd uniform over the dropped 8S bits
+template <int S>
+__device__ __forceinline__ long long tc_zfix(unsigned long long xi, unsigned long long xj, uint32_t rw) {
+    if (S == 4) return (long long)((xi * xj + (unsigned long long)rw) >> 32);
+    const unsigned __int128 pr = (unsigned __int128)xi * xj + (((unsigned long long)rw << 8) | (rw >> 24));
+    return (long long)(unsigned long long)(pr >> 40);
 }
 
 // Zs[s][pair(i,j)][t] for i fixed (blockIdx.y), 32 columns j (blockIdx.x), 128 time bins (blockIdx.z, strided).
@@ -415,23 +962,26 @@ zslice_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const 
     const int i = blockIdx.y;
     const int j0 = blockIdx.x * 32;
     if (j0 > i) return;
-    __shared__ double xs[32][130];
-    __shared__ double xi[128];
+    __shared__ unsigned long long xs[32][130];
+    __shared__ unsigned long long xi[128];
+    __shared__ uint32_t rws[128];
     const int tid = threadIdx.x;
     const int jl = tid >> 3, tq = tid & 7;
     const int j = j0 + jl;
     const int ei = tc_exponent(cmax[i]);
-    const int ej = (j < D) ? tc_exponent(cmax[j]) : 0;
-    const double scale = ldexp(1.0, 8 * S - ei - ej);
     const long long p = (long long)i * (i + 1) / 2 + j;
     for (long long tb = (long long)blockIdx.z * 128; tb < Tpad; tb += (long long)gridDim.z * 128) {
         __syncthreads();
         for (int x = tid; x < 128 * 32; x += 256) {
             const int r = x >> 5, c = x & 31;
             const long long t = tb + r;
-            xs[c][r] = (t < T && j0 + c <= i) ? Xp[t * ldx + j0 + c] : 0.0;
+            xs[c][r] = (t < T && j0 + c <= i)
+                           ? tc_xq<S>(Xp[t * ldx + j0 + c], tc_exponent(cmax[j0 + c]), j0 + c, (unsigned long long)(t_off + t)) : 0ull;
         }
-        if (tid < 128) xi[tid] = (tb + tid < T) ? Xp[(tb + tid) * ldx + i] : 0.0;
+        if (tid < 128) {
+            xi[tid] = (tb + tid < T) ? tc_xq<S>(Xp[(tb + tid) * ldx + i], ei, i, (unsigned long long)(t_off + tb + tid)) : 0ull;
+            rws[tid] = tc_rword((unsigned long long)(t_off + tb + tid));
+        }
         __syncthreads();
         if (j <= i) {
             unsigned pk[S][4];
@@ -440,7 +990,9 @@ zslice_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const 
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 unsigned d[S];
-                tc_digits<S>(xs[jl][tq * 16 + k] * xi[tq * 16 + k] * scale + tc_dither((unsigned long long)p, (unsigned long long)(t_off + tb + tq * 16 + k)), d);
+                const int tt = tq * 16 + k;
+                // (bins past the end of the recording hold xq = 0: the product dither alone never reaches bit 8S)
+                tc_digits_int<S>(tc_zfix<S>(xi[tt], xs[jl][tt], rws[tt]), d);
 #pragma unroll
                 for (int s = 0; s < S; ++s) pk[s][k >> 2] |= d[s] << (8 * (k & 3));
             }
@@ -454,11 +1006,40 @@ zslice_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const 
     }
 }
 
+// Fixed-point design for the streaming kernel (S = 4), TILED so that every TMA box of the kernel is one contiguous 1 KB
+// piece (with rows of Tpad entries a box of 8 rows touched 8 pages megabytes apart: at T = 1.25e6 the kernel ran at the
+// TLB's pace, ncu: tensor pipe 55 %, DRAM reads 10x the operands):  xq[t / 32][c][t % 32] = tc_xq(Xp[t][c]) as uint32,
+// Dp = D rounded up to 16 rows per 32-bin block (rows >= D and bins >= T are zero: the caller zeroes xq), and per bin the 64-bit addend of the builder's multiply-add: low word = tc_rword(t_off + t), high word =
+// 0x00808080 (the signed-digit offset).  Tile = 128 bins x 32 columns through smem.
+__global__ void __launch_bounds__(256)
+quantize_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const double* __restrict__ cmax,
+                uint32_t* __restrict__ xq, unsigned long long* __restrict__ rw, long long Tpad, long long t_off, int Dp) {
+    __shared__ uint32_t tile[32][129];
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * 32;
+    const long long tb = (long long)blockIdx.y * 128;
+    for (int x = tid; x < 128 * 32; x += 256) {
+        const int r = x >> 5, c = x & 31;
+        const long long t = tb + r;
+        uint32_t v = 0u;
+        if (t < T && c0 + c < D)
+            v = (uint32_t)tc_xq<4>(Xp[t * ldx + c0 + c], tc_exponent(cmax[c0 + c]), c0 + c, (unsigned long long)(t_off + t));
+        tile[c][r] = v;
+    }
+    __syncthreads();
+    for (int x = tid; x < 128 * 32; x += 256) {
+        const int c = x >> 7, r = x & 127;
+        if (c0 + c < D && tb + r < Tpad) xq[(((tb + r) >> 5) * Dp + c0 + c) * 32 + ((tb + r) & 31)] = tile[c][r];
+    }
+    if (blockIdx.x == 0 && tid < 128 && tb + tid < Tpad)
+        rw[tb + tid] = ((unsigned long long)0x00808080u << 32) | tc_rword((unsigned long long)(t_off + tb + tid));
+}
+
 // Os[s][n][t]: digits of omega[t, n] * 2^(8S - eo_n); tile = 128 time bins x 32 neurons, transposed through smem.
 template <int S>
 __global__ void __launch_bounds__(256)
 oslice_kernel(const double* __restrict__ Om, int ldo, long long T, int n_valid, const double* __restrict__ omax,
-              uint8_t* __restrict__ Os, int Npad, long long Tpad) {
+              uint8_t* __restrict__ Os, int Npad, long long Tpad, int tiled) {
     __shared__ double ws[32][130];
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * 32;
@@ -483,10 +1064,14 @@ oslice_kernel(const double* __restrict__ Om, int ldo, long long T, int n_valid, 
 #pragma unroll
         for (int s = 0; s < S; ++s) pk[s][k >> 2] |= d[s] << (8 * (k & 3));
     }
+    const long long t16 = tb + tq * 16;
 #pragma unroll
-    for (int s = 0; s < S; ++s)
-        *reinterpret_cast<uint4*>(Os + ((long long)s * Npad + n) * Tpad + tb + tq * 16) =
-            make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+    for (int s = 0; s < S; ++s) {
+        // time-major planes Os[s][n][t] (resident kernel) or K-block-major Os[s][t / 64][n][t % 64] (streaming kernels)
+        const long long off = tiled ? (((long long)s * (Tpad / TC_BK) + t16 / TC_BK) * Npad + n) * TC_BK + (t16 % TC_BK)
+                                    : ((long long)s * Npad + n) * Tpad + t16;
+        *reinterpret_cast<uint4*>(Os + off) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+    }
 }
 
 // J[n][i][j] (i >= j) = Jint[n][pair(i,j)] * 2^(ex_i + ex_j + eo_n - 8 S - 8): the operands carry 2^(8S) each and the
@@ -588,12 +1173,89 @@ int tc_launch(const uint8_t* Zs, const uint8_t* Os, long long* Jint, const TcIte
               : tc_launch_kernel<S, false>(mz, mo, Jint, sched, smem, stream);
 }
 
+// tiled fixed-point design as a 2-D uint32 tensor: inner dim = 32 bins, outer dim = (32-bin block, row) pairs; box = 32
+// bins x 8 rows = 1 KB contiguous, SWIZZLE_128B
+int ts_make_xq_map(CUtensorMap* map, const void* xq, long long Tpad, int Dp) {
+    EncodeTiledFn enc;
+    int rc = tc_encode_fn(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {32, (cuuint64_t)(Tpad / 32) * (cuuint64_t)Dp};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {32, 8};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(xq), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pyglm_set_error("cuTensorMapEncodeTiled failed (CUresult %d) for the fixed-point design, Tpad=%lld Dp=%d", (int)r, Tpad, Dp);
+        return PYGLM_ERR_CUDA;
+    }
+    return PYGLM_OK;
+}
+
+// tiled omega digit planes Os[s][Tpad / 64][Npad][64] as a 2-D byte tensor: inner dim = 64 bins, outer dim = (digit, K
+// block, neuron); box = 64 B x nt rows = one contiguous piece, SWIZZLE_64B
+int ts_make_o_map(CUtensorMap* map, const void* Os, long long Tpad, int S, int Npad, int nt) {
+    EncodeTiledFn enc;
+    int rc = tc_encode_fn(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)TC_BK, (cuuint64_t)S * (cuuint64_t)(Tpad / TC_BK) * (cuuint64_t)Npad};
+    cuuint64_t strides[1] = {(cuuint64_t)TC_BK};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)nt};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(Os), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pyglm_set_error("cuTensorMapEncodeTiled failed (CUresult %d) for the tiled omega planes, Tpad=%lld Npad=%d nt=%d", (int)r, Tpad, Npad, nt);
+        return PYGLM_ERR_CUDA;
+    }
+    return PYGLM_OK;
+}
+
+template <int S>
+int ts_launch(const uint32_t* xq, const unsigned long long* rw, const uint8_t* Os, long long* Jint, const TcItems& it, long long Tpad,
+              int max_ctas, cudaStream_t stream) {
+    CUtensorMap mx, mo;
+    int rc = ts_make_xq_map(&mx, xq, Tpad, it.Dp);
+    if (rc) return rc;
+    rc = ts_make_o_map(&mo, Os, Tpad, S, it.Npad, it.nt);
+    if (rc) return rc;
+    const int stage = (S * (TC_BM * TC_BK + tc_nt_max(S) * TC_BK) + TS_XQ_BYTES + TS_RW_BYTES + 1023) & ~1023;
+    const int smem = TS_STAGES * stage + 1024;
+    int dev = 0, sms = 0;
+    PYGLM_CUDA(cudaGetDevice(&dev));
+    PYGLM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (max_ctas > 0 && sms > max_ctas) sms = max_ctas;
+    const long long pairs = (long long)it.n_mtiles * it.n_chunks;
+    long long groups = sms / it.n_ntiles;
+    if (groups < 1) groups = 1;
+    if (groups > pairs) groups = pairs;
+    TcItems sched = it;
+    sched.n_ctas = (int)groups * it.n_ntiles;
+    // Z tiles in tensor memory when the S accumulators leave 64 TMEM columns free (nt <= 112); PYGLM_TC_ATMEM=0 keeps
+    // the tiles in shared memory (measurement, and the only form for 112 < nt <= 128)
+    static int atmem = -1;
+    if (atmem < 0) { const char* e = getenv("PYGLM_TC_ATMEM"); atmem = e ? atoi(e) : 1; }
+    if (atmem && it.nt <= TM_NT_MAX) {
+        const int tm_stage = (S * TM_NT_MAX * TC_BK + TS_XQ_BYTES + TS_RW_BYTES + 1023) & ~1023;
+        const int tm_smem = TM_STAGES * tm_stage + 1024;
+        PYGLM_CUDA(cudaFuncSetAttribute(gram_tcm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem));
+        gram_tcm_kernel<S><<<sched.n_ctas, TS_THREADS, tm_smem, stream>>>(mx, mo, rw, Jint, sched);
+    } else {
+        PYGLM_CUDA(cudaFuncSetAttribute(gram_tcs_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        gram_tcs_kernel<S><<<sched.n_ctas, TS_THREADS, smem, stream>>>(mx, mo, rw, Jint, sched);
+    }
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
 }  // namespace
 
 // Geometry of the tensor-core Gram for (D, n_valid, T, S): out[0]=M pairs, [1]=Mpad, [2]=Tpad, [3]=Npad, [4]=nt,
 // [5]=n_ntiles, [6]=n_chunks, [7]=blocks_per_chunk.  Returns 0, or an error when S is unsupported.
 extern "C" int pyglm_gram_tc_geometry(int D, int n_valid, long long T, int S, long long* out) {
-    PYGLM_CHECK_ARG(S == 3 || S == 4 || S == 5, "pyglm_gram_tc: S=%d digits unsupported (3, 4 or 5)", S);
+    PYGLM_CHECK_ARG(S == 4 || S == 5, "pyglm_gram_tc: S=%d digits unsupported (4 or 5)", S);
     PYGLM_CHECK_ARG(D > 0 && n_valid > 0 && T > 0 && out, "pyglm_gram_tc_geometry: bad arguments");
     const long long M = (long long)D * (D + 1) / 2;
     const long long Mpad = (M + TC_BM - 1) / TC_BM * TC_BM;
@@ -641,7 +1303,6 @@ extern "C" int pyglm_gram_tc_build_z_slab(const double* Xp, int ldx, long long T
     long long tb = (Tpad + 127) / 128;
     dim3 grid((D + 31) / 32, D, (unsigned)(tb > 4096 ? 4096 : tb));
     switch (S) {
-        case 3: zslice_kernel<3><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad, t_off); break;
         case 4: zslice_kernel<4><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad, t_off); break;
         case 5: zslice_kernel<5><<<grid, 256, 0, stream>>>(Xp, ldx, T, D, cmax, Zs, Mpad, Tpad, t_off); break;
         default: pyglm_set_error("pyglm_gram_tc_build_z: S=%d unsupported", S); return PYGLM_ERR_INVALID;
@@ -656,20 +1317,20 @@ extern "C" int pyglm_gram_tc_build_z(const double* Xp, int ldx, long long T, int
 }
 
 // Per sweep: digits of omega (T x ldo, n_valid columns) -> Os (S * Npad * Tpad bytes, rows >= n_valid stay zero:
-// ZEROED once by the caller); omax (n_valid doubles) and neg_flag are overwritten.
+// ZEROED once by the caller); omax (n_valid doubles) and neg_flag are overwritten.  tiled = 0: time-major planes
+// Os[s][n][t] for pyglm_gram_tc_mma; tiled = 1: K-block-major Os[s][t / 64][n][t % 64] for pyglm_gram_tc_mma_stream.
 // The digit planes alone, with the per-neuron scale given: omax (n_valid doubles, read only) must be >= every entry of
 // the column.  Time-sharded runs all-reduce (max) the slab maxima first so that every rank slices with the same scale.
 extern "C" int pyglm_gram_tc_slice_digits(const double* Om, int ldo, long long T, int n_valid, int S, const double* omax,
-                                          unsigned char* Os, int Npad, long long Tpad, cudaStream_t stream) {
+                                          unsigned char* Os, int Npad, long long Tpad, int tiled, cudaStream_t stream) {
     PYGLM_CHECK_ARG(Om && omax && Os, "pyglm_gram_tc_slice_digits: null pointer");
     PYGLM_CHECK_ARG(Tpad % TC_BK == 0 && Tpad >= T && Npad >= n_valid, "pyglm_gram_tc_slice_digits: bad geometry");
     long long gy = (Tpad + 127) / 128;
     PYGLM_CHECK_ARG(gy <= 65535, "pyglm_gram_tc_slice_digits: T too large for one launch");
     dim3 grid((n_valid + 31) / 32, (unsigned)gy);
     switch (S) {
-        case 3: oslice_kernel<3><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad); break;
-        case 4: oslice_kernel<4><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad); break;
-        case 5: oslice_kernel<5><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad); break;
+        case 4: oslice_kernel<4><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad, tiled); break;
+        case 5: oslice_kernel<5><<<grid, 256, 0, stream>>>(Om, ldo, T, n_valid, omax, Os, Npad, Tpad, tiled); break;
         default: pyglm_set_error("pyglm_gram_tc_slice_digits: S=%d unsupported", S); return PYGLM_ERR_INVALID;
     }
     PYGLM_LAUNCH_CHECK();
@@ -677,11 +1338,12 @@ extern "C" int pyglm_gram_tc_slice_digits(const double* Om, int ldo, long long T
 }
 
 extern "C" int pyglm_gram_tc_slice_omega(const double* Om, int ldo, long long T, int n_valid, int S, double* omax,
-                                         int* neg_flag, unsigned char* Os, int Npad, long long Tpad, cudaStream_t stream) {
+                                         int* neg_flag, unsigned char* Os, int Npad, long long Tpad, int tiled,
+                                         cudaStream_t stream) {
     PYGLM_CHECK_ARG(Om && omax && Os && neg_flag, "pyglm_gram_tc_slice_omega: null pointer");
     int rc = pyglm_column_max(Om, ldo, T, n_valid, omax, neg_flag, stream);
     if (rc) return rc;
-    return pyglm_gram_tc_slice_digits(Om, ldo, T, n_valid, S, omax, Os, Npad, Tpad, stream);
+    return pyglm_gram_tc_slice_digits(Om, ldo, T, n_valid, S, omax, Os, Npad, Tpad, tiled, stream);
 }
 
 // The tcgen05 integer GEMM: Jint[n][pair] = sum_t sum_{a+b<S} 256^(S-1-a-b) zs[a][pair][t] os[b][n][t]  (exact).
@@ -700,13 +1362,13 @@ static int gram_tc_mma_impl(const unsigned char* Zs, const unsigned char* Os, in
     it.M = g[0]; it.Mpad = g[1]; it.Npad = (int)g[3]; it.nt = (int)g[4]; it.n_ntiles = (int)g[5];
     it.n_chunks = (int)g[6]; it.blocks_per_chunk = (int)g[7]; it.n_blocks = (int)(g[2] / TC_BK);
     it.n_mtiles = (int)(g[1] / TC_BM); it.n_valid = n_valid; it.ldj = ldjint; it.probe = probe;
+    it.tiles = nullptr; it.D = D; it.Dp = 0;
     static int multicast = -1;
     if (multicast < 0) { const char* e = getenv("PYGLM_TC_MULTICAST"); multicast = e ? atoi(e) : 1; }
     it.multicast = multicast; it.n_ctas = 0;
     if (max_ctas < 0) { it.multicast = 0; max_ctas = (max_ctas == -1) ? 0 : -max_ctas; }   // measurement hook
     PYGLM_CUDA(cudaMemsetAsync(Jint, 0, sizeof(long long) * (size_t)n_valid * (size_t)ldjint, stream));
     switch (S) {
-        case 3: return tc_launch<3>(Zs, Os, Jint, it, g[2], max_ctas, stream);
         case 4: return tc_launch<4>(Zs, Os, Jint, it, g[2], max_ctas, stream);
         case 5: return tc_launch<5>(Zs, Os, Jint, it, g[2], max_ctas, stream);
     }
@@ -724,6 +1386,72 @@ extern "C" int pyglm_gram_tc_mma(const unsigned char* Zs, const unsigned char* O
 extern "C" int pyglm_gram_tc_mma_probe(const unsigned char* Zs, const unsigned char* Os, int D, int n_valid, long long T,
                                        int S, long long* Jint, long long ldjint, cudaStream_t stream) {
     return gram_tc_mma_impl(Zs, Os, D, n_valid, T, S, Jint, ldjint, 0, 1, stream);
+}
+
+
+// ---- streaming variant (no resident Z): pair tiles of 8 x 16 columns of the design, built in shared memory -----------
+// (i block, j block) of every pair tile that holds at least one pair j <= i < D, i block major.  Returns the number of
+// tiles; fills out[2 * k], out[2 * k + 1] for k < cap (host memory; pass cap = 0 to size the table).
+extern "C" int pyglm_gram_tc_stream_tiles(int D, int* out, int cap) {
+    int n = 0;
+    for (int ib = 0; ib * TS_TI < D; ++ib) {
+        const int i_hi = min(D - 1, ib * TS_TI + TS_TI - 1);
+        for (int jb = 0; jb * TS_TJ <= i_hi; ++jb) {
+            if (out && n < cap) { out[2 * n] = ib; out[2 * n + 1] = jb; }
+            ++n;
+        }
+    }
+    return n;
+}
+
+// Fixed-point design of a time slab, tiled: xq[Tpad / 32][Dp][32] uint32 with Dp = D rounded up to 16 (entry
+// [t / 32][c][t % 32] = column c of Xp at bin t; ZEROED by the caller), and the per-bin rounding addends rw (Tpad uint64: dither word | 0x00808080 << 32).  cmax as for pyglm_gram_tc_build_z_slab (column
+// maxima over the WHOLE recording).
+extern "C" int pyglm_gram_tc_quantize(const double* Xp, int ldx, long long T, long long t_off, int D, const double* cmax,
+                                      unsigned int* xq, unsigned long long* rw, long long Tpad, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(Xp && cmax && xq && rw && t_off >= 0, "pyglm_gram_tc_quantize: null pointer");
+    PYGLM_CHECK_ARG(D > 0 && D <= ldx && Tpad % TC_BK == 0 && Tpad >= T && T > 0, "pyglm_gram_tc_quantize: bad geometry");
+    const int Dp = (D + 15) / 16 * 16;
+    const long long gy = (Tpad + 127) / 128;
+    PYGLM_CHECK_ARG(gy <= 2147483647LL / 1, "pyglm_gram_tc_quantize: T too large");
+    dim3 grid((D + 31) / 32, 1, 1);
+    // blockIdx.y is limited to 65535: walk the time axis in slices of 65535 x 128 bins
+    for (long long y0 = 0; y0 < gy; y0 += 65535) {
+        const long long ny = (gy - y0 < 65535) ? gy - y0 : 65535;
+        grid.y = (unsigned)ny;
+        const long long tskip = y0 * 128;
+        quantize_kernel<<<grid, 256, 0, stream>>>(Xp + tskip * ldx, ldx, T - tskip, D, cmax, xq + (tskip >> 5) * Dp * 32,
+                                                  rw + tskip, Tpad - tskip, t_off + tskip, Dp);
+        PYGLM_LAUNCH_CHECK();
+    }
+    return PYGLM_OK;
+}
+
+// The integer GEMM of pyglm_gram_tc_mma with the Z digit tiles built on the fly from xq / rw (S = 4 only):
+// bit-identical Jint.  tiles: DEVICE copy of the table of pyglm_gram_tc_stream_tiles (n_tiles entries of two ints).
+// Jint: n_valid rows of pitch ldjint >= D (D + 1) / 2 int64, overwritten.
+extern "C" int pyglm_gram_tc_mma_stream(const unsigned int* xq, const unsigned long long* rw, const unsigned char* Os, int D,
+                                        int n_valid, long long T, int S, const int* tiles, int n_tiles, long long* Jint,
+                                        long long ldjint, int max_ctas, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(xq && rw && Os && tiles && Jint, "pyglm_gram_tc_mma_stream: null pointer");
+    PYGLM_CHECK_ARG(S == 4, "pyglm_gram_tc_mma_stream: S=%d unsupported (the streaming builder is 4 digits)", S);
+    long long g[8];
+    int rc = pyglm_gram_tc_geometry(D, n_valid, T, S, g);
+    if (rc) return rc;
+    PYGLM_CHECK_ARG(n_tiles == pyglm_gram_tc_stream_tiles(D, nullptr, 0), "pyglm_gram_tc_mma_stream: tile table does not match D=%d", D);
+    PYGLM_CHECK_ARG(ldjint >= g[0], "pyglm_gram_tc_mma_stream: ldjint=%lld < pairs=%lld", ldjint, g[0]);
+    PYGLM_CHECK_ARG(((uintptr_t)xq & 127) == 0 && ((uintptr_t)rw & 127) == 0 && ((uintptr_t)Os & 127) == 0,
+                    "pyglm_gram_tc_mma_stream: operands must be 128-byte aligned");
+    PYGLM_CHECK_ARG(g[2] < (1LL << 31), "pyglm_gram_tc_mma_stream: problem too large for 32-bit TMA coordinates");
+    TcItems it;
+    it.M = g[0]; it.Mpad = g[1]; it.Npad = (int)g[3]; it.nt = (int)g[4]; it.n_ntiles = (int)g[5];
+    it.n_chunks = (int)g[6]; it.blocks_per_chunk = (int)g[7]; it.n_blocks = (int)(g[2] / TC_BK);
+    it.n_mtiles = n_tiles; it.n_valid = n_valid; it.ldj = ldjint; it.probe = 0; it.multicast = 0; it.n_ctas = 0;
+    it.tiles = tiles; it.D = D; it.Dp = (D + 15) / 16 * 16;
+    PYGLM_CHECK_ARG((long long)S * it.n_blocks * it.Npad < (1LL << 31) && (g[2] / 32) * it.Dp < (1LL << 31),
+                    "pyglm_gram_tc_mma_stream: problem too large for 32-bit TMA coordinates");
+    PYGLM_CUDA(cudaMemsetAsync(Jint, 0, sizeof(long long) * (size_t)n_valid * (size_t)ldjint, stream));
+    return ts_launch<4>(xq, rw, Os, Jint, it, g[2], max_ctas, stream);
 }
 
 // J[n][i][j] (lower triangle, pitch ldj, stride_n between neurons) from the exact integer sums and the scales.

@@ -14,6 +14,8 @@ reference's sweep (models.py:166-171 -> regression.py:265-280):
 
 X, Y, psi, omega, J never leave the device; only O(N^2 B) state crosses PCIe per sweep.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -79,14 +81,17 @@ class DeviceMoments(object):
 
 
 class GibbsEngine(object):
-    def __init__(self, N, B, kernels=None, seed=0, comm=None, shard="neuron", gram="auto", gram_digits=4):
+    def __init__(self, N, B, kernels=None, seed=0, comm=None, shard="neuron", gram="auto", gram_digits=4,
+                 gram_stream="auto"):
         """gram: "fp64" = FP64 DMMA kernel (gram.cu); "tc" = tcgen05 integer-digit kernel (gram_tc.cu), checked
         against the FP64 kernel on the first sweep (<= 5e-10 relative, else one more digit, else FP64);
         "auto" = "tc" when the design is non-negative, the contraction is large enough to matter and the digit
         planes of Z fit in HBM, else "fp64".  gram_digits: radix-256 digits the tc path starts with (4 or 5)."""
         assert shard in ("neuron", "time")
-        assert gram in ("auto", "fp64", "tc") and gram_digits in (3, 4, 5)
+        assert gram in ("auto", "fp64", "tc") and gram_digits in (4, 5) and gram_stream in ("auto", True, False)
         self.gram_mode, self.gram_digits = gram, gram_digits
+        env = os.environ.get("PYGLM_TC_STREAM")
+        self.gram_stream = gram_stream if env is None else (env != "0")
         self.N, self.B = N, B
         self.D = N * B + 1
         self.ldx = pad_ldx(self.D)
@@ -160,6 +165,7 @@ class GibbsEngine(object):
         return self._ws[key]
 
     # ------------------------------------------------------------------ Gram dispatch
+    TC_STREAM_DEFAULT = False   # "auto": build Z tiles in the kernel even when the resident planes would fit
     TC_MIN_WORK = 5e9           # pairs * T * neurons below which the FP64 kernel is used (cfg2 = 9e9: tc 0.49 ms vs 1.28 ms)
     TC_ACCEPT = 5e-10           # accepted max relative deviation from the FP64 kernel (stated tolerance 1e-9, 2x margin)
 
@@ -174,20 +180,37 @@ class GibbsEngine(object):
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.K.device)
         return bool(self.comm.all_reduce_min(flag).item())
 
+    def _tc_stream(self, ds, n, digits):
+        """True: the kernel builds the Z digit tiles in shared memory (4 digits only); False: resident digit planes;
+        None: neither is possible here.  gram_stream True / False force one; "auto" streams when the planes would not
+        fit in HBM, and otherwise follows TC_STREAM_DEFAULT (the measured choice).  All ranks decide alike."""
+        free = torch.cuda.mem_get_info(self.K.device)[0]
+        fits = self._agree(gram_tc_bytes(self.D, n, ds.T, digits) < 0.9 * free)
+        if self.gram_stream is True:
+            return True if digits == 4 else None
+        if self.gram_stream is False:
+            return False if fits else None
+        if digits == 4 and (self.TC_STREAM_DEFAULT or not fits):
+            return True
+        return False if fits else None
+
     def _tc_build(self, ds, n, digits):
-        need = gram_tc_bytes(self.D, n, ds.T, digits)
+        stream = self._tc_stream(ds, n, digits)
+        if stream is None:
+            return None
+        need = gram_tc_bytes(self.D, n, ds.T, digits, stream=stream)
         free = torch.cuda.mem_get_info(self.K.device)[0]
         if not self._agree(need < 0.9 * free):
             return None
         try:
             if self._time_sharded():
-                plan = self.K.gram_tc_plan(ds.Xp, self.D, n, digits, comm=self.comm, t_off=ds.t_off)
+                plan = self.K.gram_tc_plan(ds.Xp, self.D, n, digits, comm=self.comm, t_off=ds.t_off, stream=stream)
                 # Jint with the row padding the reduce-scatter over the neuron axis needs (extra rows stay zero)
                 rows = self.comm.world * self.n_max
                 if rows != n:
                     plan.Jint = torch.zeros(rows, plan.geom["Mpad"], dtype=torch.int64, device=self.K.device)
                 return plan
-            return self.K.gram_tc_plan(ds.Xp, self.D, n, digits)
+            return self.K.gram_tc_plan(ds.Xp, self.D, n, digits, stream=stream)
         except ValueError:
             return None                  # signed design: the digits of Z assume x >= 0
 
@@ -203,7 +226,8 @@ class GibbsEngine(object):
             plan = self._tc_build(ds, n, self.gram_digits) if want else None
             if plan is None and self.gram_mode == "tc":
                 raise RuntimeError("gram='tc' needs a non-negative design and %.1f GB of free HBM"
-                                   % (gram_tc_bytes(self.D, n, ds.T, self.gram_digits) / 1e9))
+                                   % (gram_tc_bytes(self.D, n, ds.T, self.gram_digits,
+                                                    stream=self.gram_stream is True) / 1e9))
             ds.buffers[key] = plan
         return ds.buffers[key]
 
@@ -269,6 +293,65 @@ class GibbsEngine(object):
             self.K.weighted_gram(ds.Xp, omega, self.D, n, J=J)
         return J
 
+    TC_RECHECK_EVERY = 16       # sweeps between spot checks of the tensor-core Gram against the FP64 kernel
+    TC_RECHECK_NEURONS = 2      # neurons compared per spot check (rotating through the local block)
+
+    def _tc_spot_check(self, ds, omega, n, plan):
+        """The first-sweep check (_tc_verified) sees one omega; the deviation of the fixed-point Gram depends on the
+        data, and omega changes every sweep.  So every TC_RECHECK_EVERY-th use of a plan, TC_RECHECK_NEURONS neurons
+        (rotating) are recomputed by the FP64 kernel from the sweep's own omega and compared entry by entry with what
+        the tensor-core kernel has just produced (time-sharded: the slab's partial sums on both sides).  Nothing
+        waits: the worst relative deviation goes to pinned memory behind an event and is read at the start of a later
+        sweep (_tc_poll), where a deviation above TC_ACCEPT retires the plan (FP64 kernel from then on) with a warning.
+        Time-sharded ranks all-reduce (max) the figure so that they retire the plan at the same sweep."""
+        k = min(self.TC_RECHECK_NEURONS, n)
+        lo = (plan.checks * k) % max(n - k + 1, 1)
+        plan.checks += 1
+        om = self._wsbuf("tc_check_omega", (ds.T, pad_ldn(k)), zero=True)
+        om[:, :k] = omega[:, lo:lo + k]
+        J_ref = self.K.weighted_gram(ds.Xp, om, self.D, k)
+        J_tc = plan.finalize(self._wsbuf("tc_check_J", (k, self.ldx, self.ldx), zero=True),
+                             Jint=plan.Jint[lo:lo + k], omax=plan.omax[lo:lo + k])
+        if "tril" not in self._ws:
+            self._ws["tril"] = torch.tril(torch.ones(self.D, self.D, dtype=torch.bool, device=J_ref.device))
+        a, b = J_tc[:, :self.D, :self.D], J_ref[:, :self.D, :self.D]
+        dev = torch.where(self._ws["tril"] & (b != 0), (a - b).abs() / b.abs(), torch.zeros_like(b))
+        worst = dev.max().reshape(1)
+        if self._time_sharded():
+            self.comm.all_reduce_max(worst)
+        stage = self._pinned("tc_check", (1,), torch.float64)
+        stage.copy_(worst, non_blocking=True)
+        ev = torch.cuda.Event() if self.K.device.type == "cuda" else None
+        if ev is not None:
+            ev.record()
+        self._tc_pending_check = (ev, stage, ds, n, plan, self.calls)
+
+    def _tc_poll(self, force=False):
+        """Read a finished spot check (see _tc_spot_check).  Multi-rank runs decide at a fixed sweep distance from the
+        check (waiting for the event if need be) so that every rank switches kernels at the same sweep."""
+        pend = getattr(self, "_tc_pending_check", None)
+        if pend is None:
+            return
+        ev, stage, ds, n, plan, at_call = pend
+        if self.comm.world > 1 or force:
+            if not force and self.calls < at_call + 2:
+                return
+            if ev is not None:
+                ev.synchronize()
+        elif ev is not None and not ev.query():
+            return
+        self._tc_pending_check = None
+        worst = float(stage[0])
+        plan.max_rel_dev_spot = max(worst, plan.max_rel_dev_spot or 0.0)
+        if not worst <= self.TC_ACCEPT:
+            import warnings
+            warnings.warn("tensor-core Gram deviates from the FP64 kernel by %.2e (> %.1e) on a spot check: "
+                          "falling back to the FP64 kernel for this data set" % (worst, self.TC_ACCEPT))
+            if self.gram_mode == "tc":
+                raise RuntimeError("gram='tc': spot check of the integer-digit Gram failed (%.2e)" % worst)
+            ds.buffers[("tc_plan", n)] = None
+            self._pending = None
+
     def weighted_gram(self, ds, omega, n, J):
         """J (rows of the scan block) = this dataset's weighted Gram.  Neuron-sharded / single GPU: n = local
         neurons, J has n rows.  Time-sharded: n = N, the slab's partial sums of ALL neurons are reduce-scattered
@@ -278,7 +361,12 @@ class GibbsEngine(object):
         if plan is not None and not plan.verified:
             plan = self._tc_verified(ds, omega, n, plan)
         if plan is not None:
-            return self._gram_tc(plan, omega, J)
+            self._gram_tc(plan, omega, J)
+            plan.uses += 1
+            if self.TC_RECHECK_EVERY and plan.uses % self.TC_RECHECK_EVERY == 0 \
+                    and getattr(self, "_tc_pending_check", None) is None:
+                self._tc_spot_check(ds, omega, n, plan)
+            return J
         return self._gram_fp64(ds, omega, n, J)
 
     # ------------------------------------------------------------------ coefficients
@@ -317,6 +405,15 @@ class GibbsEngine(object):
         return ds.h_cache[key]
 
     # ------------------------------------------------------------------ the sweep
+    # Philox call ids of sweep k: k * CALL_STRIDE + (index of the data set) for the PG draws, k * CALL_STRIDE +
+    # CALL_STRIDE - 1 for the scan's permutation / uniforms / normals.
+    CALL_STRIDE = 64
+
+    def _check_call_ids(self, datasets):
+        if len(datasets) >= self.CALL_STRIDE - 1:
+            raise ValueError("at most %d data sets per model: the Philox call ids of a sweep are laid out in strides "
+                             "of %d (PG draws of data set i, then the scan)" % (self.CALL_STRIDE - 2, self.CALL_STRIDE))
+
     def _augment(self, datasets, Wt, call_base):
         """psi -> omega ~ PG(1, psi) -> J for the scan block, for every dataset (regression.py:496-508, :225-262).
         Everything is enqueued on the current stream; nothing here waits for the device."""
@@ -409,7 +506,9 @@ class GibbsEngine(object):
         nP, nS = p_hi - p_lo, s_hi - s_lo
         NB = N * B
         self.calls += 1
-        call_base = self.calls * 64
+        call_base = self.calls * self.CALL_STRIDE
+        self._check_call_ids(datasets)
+        self._tc_poll()
 
         J_S = h_S = None
         if datasets:
@@ -435,7 +534,7 @@ class GibbsEngine(object):
             a_host[det] = np.round(hypers["rho"][s_lo:s_hi][det]).astype(np.uint8)
             prior, a_dev, do_scan_dev = self._upload_priors(pr, a_host, do_scan)
             if self.inject is None:
-                perm, us, z = K.scan_randomness(N, B, nS, s_lo, self.seed, call_base + 63)
+                perm, us, z = K.scan_randomness(N, B, nS, s_lo, self.seed, call_base + self.CALL_STRIDE - 1)
             else:
                 perm = K.to_device(np.asarray(self.inject["perm"][s_lo:s_hi], dtype=np.int32))
                 us = K.to_device(np.asarray(self.inject["us"][s_lo:s_hi], dtype=np.float64))
@@ -471,7 +570,7 @@ class GibbsEngine(object):
             Wt_next = self.build_Wt_device(state, p_lo, p_hi)
             if nS > 0 and datasets:
                 self._mark("exchange", e4)
-            pend_J = self._augment(datasets, Wt_next, call_base + 64)
+            pend_J = self._augment(datasets, Wt_next, call_base + self.CALL_STRIDE)
             if mom is not None and mom.rates:              # psi of the NEW state is already in the buffers
                 for di, ds in enumerate(datasets):
                     mom.add_rates(di, self._buf(ds, "psi", (ds.T, Wt_next.shape[1])), nP)
@@ -503,23 +602,23 @@ class GibbsEngine(object):
     def _gaussian_stats(self, datasets):
         """Sweep-invariant X~^T X~ (ldx, ldx), X~^T Y (N, ldx) and the number of bins, summed over the data sets
         (regression.py:225-262 with omega = 1/eta, kappa = y/eta factored out: both are sums over time only)."""
-        key = ("gauss", tuple(id(ds) for ds in datasets))
-        if self._ws.get("gauss_key") != key:
-            K, N, D = self.K, self.N, self.D
-            G = H = None
-            T = 0
-            for ds in datasets:
+        K, N, D = self.K, self.N, self.D
+        G = H = None
+        T = 0
+        for ds in datasets:
+            # cached ON the data set (an id()-keyed engine cache could be hit by a new object reusing the address)
+            if "gauss" not in ds.buffers:
                 ones = K.zeros(ds.T, pad_ldn(1))
                 ones[:, 0] = 1.0
                 Gd = K.weighted_gram(ds.Xp, ones, D, 1)[0]
                 Yp = K.zeros(ds.T, pad_ldn(N))
                 Yp[:, :N] = ds.Y
-                Hd = K.xt_kappa(ds.Xp, Yp, D, N)
-                G = Gd if G is None else G + Gd
-                H = Hd if H is None else H + Hd
-                T += ds.T
-            self._ws["gauss_key"], self._ws["gauss_val"] = key, (G, H, T)
-        return self._ws["gauss_val"]
+                ds.buffers["gauss"] = (Gd, K.xt_kappa(ds.Xp, Yp, D, N))
+            Gd, Hd = ds.buffers["gauss"]
+            G = Gd if G is None else G + Gd
+            H = Hd if H is None else H + Hd
+            T += ds.T
+        return G, H, T
 
     def residual_ss(self, datasets, A, W, b):
         """sum_t (y_{t,n} - psi_{t,n})^2 for every neuron, over all data sets: (N,) host array."""
@@ -545,15 +644,21 @@ class GibbsEngine(object):
         nS = s_hi - s_lo
         NB = N * B
         self.calls += 1
-        call_base = self.calls * 64
+        call_base = self.calls * self.CALL_STRIDE
+        self._check_call_ids(datasets)
         self._pending = None
         width = N + NB + 2
         state = K.zeros(self.n_max if comm.world > 1 else nS, width)
-        if nS > 0 and datasets:
-            G, H, _ = self._gaussian_stats(datasets)
-            inv_eta = K.to_device(1.0 / np.asarray(eta, dtype=np.float64)[s_lo:s_hi])
-            J_S = G.unsqueeze(0) * inv_eta[:, None, None]
-            h_S = H[s_lo:s_hi] * inv_eta[:, None]
+        if nS > 0:
+            if datasets:
+                G, H, _ = self._gaussian_stats(datasets)
+                inv_eta = K.to_device(1.0 / np.asarray(eta, dtype=np.float64)[s_lo:s_hi])
+                J_S = G.unsqueeze(0) * inv_eta[:, None, None]
+                h_S = H[s_lo:s_hi] * inv_eta[:, None]
+            else:
+                # no data: the posterior is the prior, as in sweep() (regression.py:237 with datas = [])
+                J_S = self._wsbuf("J_nodata", (nS, ldx, ldx), zero=True)
+                h_S = self._wsbuf("h_nodata", (nS, ldx), zero=True)
             pr = prior_arrays(hypers["rho"][s_lo:s_hi], hypers["mu_w"][s_lo:s_hi], hypers["S_w"][s_lo:s_hi],
                               hypers["mu_b"][s_lo:s_hi], hypers["S_b"][s_lo:s_hi])
             do_scan = pr.pop("do_scan")
@@ -562,7 +667,7 @@ class GibbsEngine(object):
             a_host[det] = np.round(hypers["rho"][s_lo:s_hi][det]).astype(np.uint8)
             prior, a_dev, do_scan_dev = self._upload_priors(pr, a_host, do_scan)
             if self.inject is None:
-                perm, us, z = K.scan_randomness(N, B, nS, s_lo, self.seed, call_base + 63)
+                perm, us, z = K.scan_randomness(N, B, nS, s_lo, self.seed, call_base + self.CALL_STRIDE - 1)
             else:
                 perm = K.to_device(np.asarray(self.inject["perm"][s_lo:s_hi], dtype=np.int32))
                 us = K.to_device(np.asarray(self.inject["us"][s_lo:s_hi], dtype=np.float64))
@@ -586,7 +691,8 @@ class GibbsEngine(object):
         b_out = host[:, N + NB].copy()
         if self.moments is not None:
             self.moments.add_state(state, N + NB + 1)
-        return A_out, W_out, b_out, self.residual_ss(datasets, A_out, W_out, b_out)
+        rss = self.residual_ss(datasets, A_out, W_out, b_out) if datasets else np.zeros(N)
+        return A_out, W_out, b_out, rss
 
     def activations(self, ds, A, W, b):
         """(T, N) psi for one data set: the mean of a Gaussian regression (regression.py:429-430)."""
@@ -601,18 +707,17 @@ class GibbsEngine(object):
         """Likelihood h for the scan block, summed over datasets (and over time slabs when time-sharded)."""
         s_lo, s_hi = self.scan_lo, self.scan_hi
         if self.shard == "time" and self.comm.world > 1:
-            key = "h_time"
-            if key not in self._ws:
-                h_all = None
-                for ds in datasets:
-                    hd = self._h_lkhd(ds, 0, self.N)
-                    h_all = hd.clone() if h_all is None else h_all + hd
-                self.comm.all_reduce_sum(h_all)
-                self._ws[key] = (len(datasets), h_all[s_lo:s_hi].contiguous())
-            n_ds, h = self._ws[key]
-            if n_ds != len(datasets):
-                del self._ws[key]
-                return self._h_for_scan(datasets)
+            # the slab sums, all-reduced once per data set and kept ON the data set (h_cache): replacing a data_list
+            # entry can then never leave a stale vector behind
+            h = None
+            for ds in datasets:
+                key = ("time_total", s_lo, s_hi)
+                if key not in ds.h_cache:
+                    h_all = self._h_lkhd(ds, 0, self.N).clone()
+                    self.comm.all_reduce_sum(h_all)
+                    ds.h_cache[key] = h_all[s_lo:s_hi].contiguous()
+                    del ds.h_cache[(0, self.N)]
+                h = ds.h_cache[key] if h is None else h + ds.h_cache[key]
             return h
         h = None
         for ds in datasets:

@@ -197,11 +197,22 @@ class CudaKernels(object):
         self._call("pyglm_column_max", self._p(A), ld, T, ncols, self._p(cmax), self._p(neg), self._stream())
         return cmax, bool(neg.item())
 
-    def gram_tc_plan(self, Xp, D, n_valid, S=4, comm=None, t_off=0):
-        """Build the sweep-invariant digit planes of Z = X~_i X~_j (once per dataset) and allocate the per-sweep
-        buffers of the tensor-core Gram.  Raises ValueError when the design has negative entries.  comm / t_off:
+    def gram_tc_plan(self, Xp, D, n_valid, S=4, comm=None, t_off=0, stream=False):
+        """Sweep-invariant operand of the tensor-core Gram (once per dataset) and its per-sweep buffers.
+        stream=False: the digit planes of Z = X~_i X~_j stay resident in HBM (S * pairs * T bytes); stream=True: only
+        the fixed-point design (4 * D * T bytes) is kept and the kernel builds the Z tiles in shared memory (S = 4).
+        Both give the same integer sums.  Raises ValueError when the design has negative entries.  comm / t_off:
         time-sharded runs (Xp is the slab starting at global bin t_off; scales are all-reduced over `comm`)."""
-        return TcGramPlan(self, Xp, D, n_valid, S, comm=comm, t_off=t_off)
+        return TcGramPlan(self, Xp, D, n_valid, S, comm=comm, t_off=t_off, stream=stream)
+
+    def gram_tc_stream_tiles(self, D):
+        key = ("tc_stream_tiles", D)
+        if key not in self._tiles:
+            n = self.lib.pyglm_gram_tc_stream_tiles(D, None, 0)
+            buf = np.zeros((n, 2), dtype=np.int32)
+            self.lib.pyglm_gram_tc_stream_tiles(D, buf.ctypes.data_as(ctypes.c_void_p), n)
+            self._tiles[key] = self.to_device(buf)
+        return self._tiles[key]
 
     # ------------------------------------------------------------------ (6) forward simulation
     def generate(self, Wm, bias, basis, T, seed, call_id, want_uniforms=False, gauss_sd=-1.0):
@@ -252,25 +263,34 @@ class CudaKernels(object):
         return W, bias, logodds, ml, status
 
 
-def gram_tc_bytes(D, n_valid, T, S=4):
-    """HBM bytes the tensor-core Gram keeps resident for one dataset (digit planes of Z and omega, Jint)."""
+def gram_tc_bytes(D, n_valid, T, S=4, stream=False):
+    """HBM bytes the tensor-core Gram keeps resident for one dataset: digit planes of Z (resident mode) or the
+    fixed-point design and the rounding addends (streaming mode), digit planes of omega, Jint."""
     M = D * (D + 1) // 2
     Mpad, Tpad = round_up(M, 128), round_up(T, 64)
-    return S * Mpad * Tpad + S * round_up(n_valid, 16) * Tpad * 2 + n_valid * Mpad * 8
+    operand = (4 * round_up(D, 16) + 8) * Tpad if stream else S * Mpad * Tpad
+    return operand + S * round_up(n_valid, 16) * Tpad * 2 + n_valid * Mpad * 8
 
 
 class TcGramPlan(object):
     """Resident state of the tcgen05 Gram for one dataset: Zs (S, Mpad, Tpad) uint8 digit planes of the
-    Khatri-Rao operand (built once), Os (S, Npad, Tpad) digit planes of omega and Jint (n, Mpad) int64 (per sweep).
+    Khatri-Rao operand (built once) -- or, in streaming mode, xq (D, Tpad) uint32 fixed-point design + rw (Tpad)
+    rounding addends, from which the kernel builds the same digit tiles in shared memory -- Os (S, Npad, Tpad) digit
+    planes of omega and Jint (n, Mpad) int64 (per sweep).
 
     Time-sharded runs pass `comm` and the slab's global offset `t_off`: the fixed-point scales (column maxima of X
     and of omega) are all-reduced (max) over the ranks and the rounding dither is keyed by the global time bin, so
     the integer partial sums of the slabs add up -- exactly, in int64 -- to the Jint a single GPU would compute."""
 
-    def __init__(self, K, Xp, D, n_valid, S=4, comm=None, t_off=0):
+    def __init__(self, K, Xp, D, n_valid, S=4, comm=None, t_off=0, stream=False):
         self.K, self.D, self.n, self.S = K, D, n_valid, S
+        self.stream = bool(stream)
+        if self.stream and S != 4:
+            raise ValueError("the streaming tensor-core Gram builds 4-digit tiles (S=4), not S=%d" % S)
         self.comm = comm if (comm is not None and comm.world > 1) else None
         self.verified, self.max_rel_dev = False, None      # set by GibbsEngine._tc_verified
+        self.uses = self.checks = 0                        # sweeps served / spot checks run (GibbsEngine._tc_spot_check)
+        self.max_rel_dev_spot = None
         self.T, self.ldx = Xp.shape
         g = K.gram_tc_geometry(D, n_valid, self.T, S)
         self.geom = g
@@ -282,9 +302,18 @@ class TcGramPlan(object):
             self.comm.all_reduce_max(self.neg)
         if bool(self.neg.item()):
             raise ValueError("tensor-core Gram needs a non-negative design matrix")
-        self.Zs = torch.zeros(S, g["Mpad"], g["Tpad"], dtype=torch.uint8, device=K.device)
-        K._call("pyglm_gram_tc_build_z_slab", K._p(Xp), self.ldx, self.T, int(t_off), D, K._p(self.cmax), S,
-                K._p(self.Zs), g["Mpad"], g["Tpad"], K._stream())
+        if self.stream:
+            self.Zs = None
+            # tiled: xq[t // 32][column][t % 32], Dp = D rounded up to 16 rows per block        (uint32 bit patterns)
+            self.xq = torch.zeros(g["Tpad"] // 32, round_up(D, 16), 32, dtype=torch.int32, device=K.device)
+            self.rw = torch.empty(g["Tpad"], dtype=torch.int64, device=K.device)          # uint64 bit patterns
+            self.tiles = K.gram_tc_stream_tiles(D)
+            K._call("pyglm_gram_tc_quantize", K._p(Xp), self.ldx, self.T, int(t_off), D, K._p(self.cmax),
+                    K._p(self.xq), K._p(self.rw), g["Tpad"], K._stream())
+        else:
+            self.Zs = torch.zeros(S, g["Mpad"], g["Tpad"], dtype=torch.uint8, device=K.device)
+            K._call("pyglm_gram_tc_build_z_slab", K._p(Xp), self.ldx, self.T, int(t_off), D, K._p(self.cmax), S,
+                    K._p(self.Zs), g["Mpad"], g["Tpad"], K._stream())
         self.Os = torch.zeros(S, g["Npad"], g["Tpad"], dtype=torch.uint8, device=K.device)
         self.omax = K.empty(n_valid)
         self.Jint = K.empty(n_valid, g["Mpad"], dtype=torch.int64)
@@ -293,23 +322,28 @@ class TcGramPlan(object):
         K, g = self.K, self.geom
         if self.comm is None:
             K._call("pyglm_gram_tc_slice_omega", K._p(Om), Om.shape[1], self.T, self.n, self.S, K._p(self.omax),
-                    K._p(self.neg), K._p(self.Os), g["Npad"], g["Tpad"], K._stream(), launches=2)
+                    K._p(self.neg), K._p(self.Os), g["Npad"], g["Tpad"], int(self.stream), K._stream(), launches=2)
             return
         K._call("pyglm_column_max", K._p(Om), Om.shape[1], self.T, self.n, K._p(self.omax), K._p(self.neg),
                 K._stream())
         self.comm.all_reduce_max(self.omax)
         K._call("pyglm_gram_tc_slice_digits", K._p(Om), Om.shape[1], self.T, self.n, self.S, K._p(self.omax),
-                K._p(self.Os), g["Npad"], g["Tpad"], K._stream())
+                K._p(self.Os), g["Npad"], g["Tpad"], int(self.stream), K._stream())
 
     def mma(self, max_ctas=0):
         K, g = self.K, self.geom
-        K._call("pyglm_gram_tc_mma", K._p(self.Zs), K._p(self.Os), self.D, self.n, self.T, self.S, K._p(self.Jint),
-                g["Mpad"], max_ctas, K._stream())
+        if self.stream:
+            K._call("pyglm_gram_tc_mma_stream", K._p(self.xq), K._p(self.rw), K._p(self.Os), self.D, self.n, self.T,
+                    self.S, K._p(self.tiles), self.tiles.shape[0], K._p(self.Jint), g["Mpad"], max_ctas, K._stream())
+        else:
+            K._call("pyglm_gram_tc_mma", K._p(self.Zs), K._p(self.Os), self.D, self.n, self.T, self.S,
+                    K._p(self.Jint), g["Mpad"], max_ctas, K._stream())
         return self.Jint
 
     def mma_probe(self):
         """Issue-rate probe of the MMA schedule (no loads, no atomics): measures the int8 tensor-pipe peak."""
         K, g = self.K, self.geom
+        assert not self.stream, "the issue-rate probe belongs to the resident kernel"
         K._call("pyglm_gram_tc_mma_probe", K._p(self.Zs), K._p(self.Os), self.D, self.n, self.T, self.S,
                 K._p(self.Jint), g["Mpad"], K._stream())
 

@@ -37,7 +37,8 @@ class NonlinearAutoregressiveModel(object):
     """The neuroscience "GLM": a nonlinear vector autoregression, one regression per observed dimension
     (models.py:8-201)."""
 
-    def __init__(self, N, regressions, basis=None, B=10, seed=None, shard="neuron", comm=None, gram="auto"):
+    def __init__(self, N, regressions, basis=None, B=10, seed=None, shard="neuron", comm=None, gram="auto",
+                 gram_stream="auto"):
         self.N = N
         assert len(regressions) == N
         self.regressions = regressions
@@ -53,6 +54,7 @@ class NonlinearAutoregressiveModel(object):
         self._shard = shard
         self._comm = comm
         self._gram = gram
+        self._gram_stream = gram_stream
         self._engine = None
         self._dev = {}           # (id(X), id(Y)) -> (X, Y, DeviceDataset): keeps the keys alive
 
@@ -75,8 +77,38 @@ class NonlinearAutoregressiveModel(object):
         if self._engine is None:
             from .engine import GibbsEngine
             self._engine = GibbsEngine(self.N, self.B, seed=self._seed, comm=self._comm, shard=self._shard,
-                                       gram=self._gram)
+                                       gram=self._gram, gram_stream=self._gram_stream)
         return self._engine
+
+    def _sync_ranks(self):
+        """Multi-GPU runs: every rank continues from RANK 0's randomness and state -- the engine's Philox seed, numpy's
+        global RNG state (the host network step and the eta draws use it), the regressions' (a, W, b, eta) and the
+        network's latent state -- so that generate(), the first partial Grams of a time-sharded sweep and every host
+        draw agree across ranks whatever each rank's own seeding was.  Collective; runs once, before the first sweep
+        or simulation.  The chain is the one a single process with rank 0's seeds would produce."""
+        if getattr(self, "_ranks_synced", False):
+            return
+        self._ranks_synced = True
+        eng = self.engine
+        comm = eng.comm
+        if comm.world == 1:
+            return
+        regs = self.regressions
+        mine = None
+        if comm.rank == 0:
+            mine = dict(seed=eng.seed, rng=np.random.get_state(), A=self.adjacency, W=self.weights, b=self.biases,
+                        eta=[getattr(r, "eta", None) for r in regs],
+                        net=self.network.get_state() if hasattr(getattr(self, "network", None), "get_state") else None)
+        st = comm.broadcast_object(mine)
+        eng.seed = st["seed"]
+        np.random.set_state(st["rng"])
+        for n, r in enumerate(regs):
+            r.a, r.W, r.b = st["A"][n].copy(), st["W"][n].copy(), st["b"][n:n + 1].copy()
+            if st["eta"][n] is not None:
+                r.eta = st["eta"][n]
+        if st["net"] is not None:
+            self.network.set_state(st["net"])
+        self._state_src = None
 
     def _time_slab(self, T):
         eng = self.engine
@@ -201,6 +233,7 @@ class NonlinearAutoregressiveModel(object):
         L, B = basis.shape
         assert not np.allclose(np.flipud(basis), self.basis)
         from .engine import DeviceDataset
+        self._sync_ranks()
         eng = self.engine
         K = eng.K
         self._generated = getattr(self, "_generated", 0) + 1
@@ -280,6 +313,7 @@ class NonlinearAutoregressiveModel(object):
 
     def resample_regressions(self):
         """All N regressions in one device sweep (they are conditionally independent given the data)."""
+        self._sync_ranks()
         A, W, b = self._host_state()
         if self._gaussian:
             dsets = self._device_datasets()
@@ -321,16 +355,11 @@ class HierarchicalNonlinearAutoregressiveModel(NonlinearAutoregressiveModel):
         """Host step (models.py:228-236).  sigma_W / mu_W / rho are built once, not once per neuron as the
         reference's property accesses do."""
         net = self.network
-        comm = self.engine.comm if self._engine is not None else None
-        if comm is not None and comm.world > 1 and not getattr(self, "_rng_synced", False):
-            # Every rank draws the (tiny) network step itself, from the SAME stream: rank 0's numpy global state is
-            # handed to all ranks once, after which identical inputs (the all-gathered A, W) give identical draws on
-            # every rank -- no per-sweep host collective on the critical path between two scans.  The chain is the
-            # one a single process with rank 0's seed would produce.
-            np.random.set_state(comm.broadcast_object(np.random.get_state() if comm.rank == 0 else None))
-            # priors that carry latent state from sweep to sweep (block labels, locations) also start from rank 0's
-            net.set_state(comm.broadcast_object(net.get_state() if comm.rank == 0 else None))
-            self._rng_synced = True
+        # Every rank draws the (tiny) network step itself, from the SAME stream: _sync_ranks() handed rank 0's numpy
+        # state and network state to all ranks once, after which identical inputs (the all-gathered A, W) give
+        # identical draws on every rank -- no per-sweep host collective on the critical path between two scans.
+        if self._engine is not None:
+            self._sync_ranks()
         net.resample((self.adjacency, self.weights))
         sigma_W, mu_W, rho = net.sigma_W, net.mu_W, net.rho
         N, B = self.N, self.B

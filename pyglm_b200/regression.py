@@ -33,7 +33,9 @@ class _SparseScalarRegressionBase(object):
             self._W[n] = self._a[n] * npr.multivariate_normal(self.mu_w[n], self.S_w[n])
         self._b = np.atleast_1d(npr.multivariate_normal(self.mu_b, self.S_b)).astype(np.float64)
         # device RNG stream of this regression when used standalone
-        self._seed = int(npr.randint(2 ** 16, size=1)[0]) + (id(self) & 0xFFFF) * 65536
+        # (drawn from numpy's global state only, like the reference's PG seeds, regression.py:476: reproducible
+        # under np.random.seed)
+        self._seed = int(npr.randint(2 ** 31 - 1))
         self._calls = 0
 
     # ---- state: plain writable numpy arrays

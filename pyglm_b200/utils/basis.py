@@ -35,6 +35,18 @@ def cosine_basis(B, L=100, orth=False, norm=True, n_eye=0, a=1.0 / 120, b=0.5):
     return table
 
 
+def interpolate_basis(basis, dt, dt_max, norm=True, allow_instantaneous=False):
+    """Resample an (L, B) basis defined on [0, dt_max] at bin width dt (pyglm/utils/basis.py:36-58; host, unused by
+    the sampler).  norm: every column integrates to one; a zero row is prepended unless allow_instantaneous."""
+    L, B = basis.shape
+    t_new = np.arange(0.0, dt_max, step=dt)
+    t_old = np.linspace(0.0, dt_max, L)
+    out = np.column_stack([np.interp(t_new, t_old, basis[:, b]) for b in range(B)])
+    if norm:
+        out = out / (dt * out.sum(axis=0))
+    return out if allow_instantaneous else np.vstack((np.zeros((1, B)), out))
+
+
 def convolve_with_basis(S, basis):
     """X[t, n, b] = sum_{l=1..L} basis[l-1, b] * S[t-l, n]  ->  (T, N, B) float64 host array.
 

@@ -228,30 +228,43 @@ def test_weighted_gram_matches_oracle(K, T, N, B, n_loc, nslabs):
 
 
 # ----------------------------------------------------------------------------- (3') weighted Gram on tcgen05
-def _tc_inputs(K, T, N, B, n_loc, seed):
+def _tc_inputs(K, T, N, B, n_loc, seed, pg=False, L=20):
+    """Design and weights for the tensor-core Gram tests.  pg=False: weights 0.01 + u^3 (max ~1, median 0.13: harsher
+    on the fixed-point scale than anything the sampler produces; used by the bit-exact integer tests).  pg=True: the
+    sampler's own distribution, omega ~ PG(1, psi) with psi ~ N(-2, 1) (oracle draws).  L: basis length -- every
+    configuration of BASELINE.json has L = 100; the short default makes the filtered trains peakier, which costs the
+    four-digit Gram about a factor four in accuracy (the engine measures this per data set and adds a digit)."""
     from pyglm_b200.kernels import pad_ldn
     rng = np.random.default_rng(seed)
     Y = spikes(T, N, seed=seed)
-    L = 20
     basis = O.cosine_basis(B, L) / L
     Xp = design(K, Y, basis)
     X = O.convolve_with_basis(Y, basis).reshape(T, N * B)
     om = np.zeros((T, pad_ldn(n_loc)))
-    om[:, :n_loc] = 0.01 + rng.random((T, n_loc)) ** 3          # skewed like PG draws, max ~1
+    if pg:
+        om[:, :n_loc] = O.pg1_draw(rng.standard_normal(T * n_loc) - 2.0, seed, 1).reshape(T, n_loc)
+    else:
+        om[:, :n_loc] = 0.01 + rng.random((T, n_loc)) ** 3
     return Xp, X, om
 
 
-@pytest.mark.parametrize("T,N,B,n_loc,S", [(1000, 5, 2, 7, 4), (333, 3, 1, 3, 3), (700, 8, 2, 20, 5),
-                                           (130, 4, 3, 33, 4)])
+@pytest.mark.parametrize("T,N,B,n_loc,S", [(1000, 5, 2, 7, 4), (333, 3, 1, 3, 4), (700, 8, 2, 20, 5),
+                                           (130, 4, 3, 33, 4),
+                                           # 128 < n_loc <= 256 with S = 4: two neuron tiles -> the 2-CTA cluster
+                                           # instantiation with TMA multicast of the Z tiles (what cfg3 runs)
+                                           (3000, 6, 2, 200, 4), (777, 4, 1, 129, 4), (20000, 3, 2, 256, 4)])
 def test_gram_tc_integer_sums_are_exact(K, T, N, B, n_loc, S):
-    """Digit planes and the tcgen05 int32/int64 sums against the numpy emulation: bit-exact (integer work)."""
+    """Digit planes and the tcgen05 int32/int64 sums against the numpy emulation: bit-exact (integer work).  With four
+    digits the streaming kernel (Z tiles built in shared memory from the fixed-point design) must return the same
+    integers as the resident-plane kernel."""
     Xp, X, om = _tc_inputs(K, T, N, B, n_loc, seed=T)
     D = N * B + 1
     plan = K.gram_tc_plan(Xp, D, n_loc, S)
     Xt = Xp.cpu().numpy()[:, :D]
     g = plan.geom
     Jint_ref, J_ref = O.tc_gram_reference(Xt, om[:, :n_loc], S)
-    plan.slice_omega(K.to_device(om))
+    om_d = K.to_device(om)
+    plan.slice_omega(om_d)
     Zs = plan.Zs.cpu().numpy()
     ex = [O.tc_exponent(c) for c in Xt.max(0)]
     for (i, j) in [(0, 0), (D - 1, 0), (D - 1, D - 1), (D // 2, D // 3)]:
@@ -263,13 +276,51 @@ def test_gram_tc_integer_sums_are_exact(K, T, N, B, n_loc, S):
     np.testing.assert_array_equal(Jint[:, :g["M"]], Jint_ref)
     J = plan.finalize(K.zeros(n_loc, plan.ldx, plan.ldx)).cpu().numpy()
     np.testing.assert_array_equal(np.tril(J[:, :D, :D]), J_ref)
+    if S == 4:
+        splan = K.gram_tc_plan(Xp, D, n_loc, S, stream=True)
+        # tiled fixed-point design xq[t // 32][column][t % 32] -> (column, t)
+        xq = splan.xq.cpu().numpy().view(np.uint32).transpose(1, 0, 2).reshape(splan.xq.shape[1], -1)
+        for i in (0, D // 2, D - 1):
+            np.testing.assert_array_equal(xq[i, :T], O.tc_xq(Xt, i, ex, S).astype(np.uint32))
+        assert xq[:, T:].max(initial=0) == 0 and xq[D:].max(initial=0) == 0
+        rw = splan.rw.cpu().numpy().view(np.uint64)
+        np.testing.assert_array_equal(rw[:T], O.tc_rword(np.arange(T)) | np.uint64(0x00808080 << 32))
+        splan.slice_omega(om_d)
+        Jint_s = splan.mma().cpu().numpy()
+        np.testing.assert_array_equal(Jint_s[:, :g["M"]], Jint_ref)
+
+
+@pytest.mark.parametrize("T,N,B,n_loc", [(70000, 40, 2, 100), (60000, 70, 3, 37), (50000, 100, 2, 200),
+                                         (150000, 30, 1, 125)])
+def test_gram_tc_streaming_equals_resident(K, T, N, B, n_loc):
+    """Larger shapes (several pair tiles per i block, several time chunks, one and two neuron tiles): the kernel that
+    builds its Z tiles in shared memory against the one that streams resident planes -- identical int64 sums -- and
+    against the oracle's FP64 Gram for a few neurons."""
+    Xp, X, om = _tc_inputs(K, T, N, B, n_loc, seed=T + 7, pg=True, L=100)
+    D = N * B + 1
+    om_d = K.to_device(om)
+    res = K.gram_tc_plan(Xp, D, n_loc, 4)
+    res.slice_omega(om_d)
+    Jint_r = res.mma().clone()
+    del res
+    st = K.gram_tc_plan(Xp, D, n_loc, 4, stream=True)
+    st.slice_omega(om_d)
+    Jint_s = st.mma()
+    assert torch.equal(Jint_s, Jint_r)
+    J = st.finalize(K.zeros(n_loc, st.ldx, st.ldx)).cpu().numpy()
+    for j in (0, n_loc // 2, n_loc - 1):
+        Jr, _ = O.lkhd_sufficient_statistics(X, om[:, j], np.zeros(T))
+        np.testing.assert_allclose(np.tril(J[j, :D, :D]), np.tril(Jr), rtol=RTOL, atol=0)
 
 
 @pytest.mark.parametrize("T,N,B,n_loc,S", [(40000, 16, 2, 40, 4), (20000, 10, 2, 200, 5), (5000, 27, 3, 27, 5),
-                                           (60000, 6, 2, 12, 5), (100000, 12, 2, 24, 4)])
+                                           (60000, 6, 2, 12, 5), (100000, 12, 2, 24, 4),
+                                           # the multicast instantiation (S = 4, two neuron tiles), VERDICT r1 item 1a
+                                           (100000, 30, 2, 200, 4), (70000, 40, 2, 150, 4)])
 def test_gram_tc_matches_oracle(K, T, N, B, n_loc, S):
     """J from the tensor-core kernel against the oracle's FP64 X^T diag(omega) X (regression.py:251-256): <= 1e-9."""
-    Xp, X, om = _tc_inputs(K, T, N, B, n_loc, seed=T + 1)
+    big = n_loc > 128 and S == 4                  # the benchmark's regime: PG-distributed weights, L = 100 basis
+    Xp, X, om = _tc_inputs(K, T, N, B, n_loc, seed=T + 1, pg=big, L=100 if big else 20)
     D = N * B + 1
     plan = K.gram_tc_plan(Xp, D, n_loc, S)
     J = plan.gram(K.to_device(om)).cpu().numpy()
@@ -278,6 +329,37 @@ def test_gram_tc_matches_oracle(K, T, N, B, n_loc, S):
     for j in list(range(min(n_loc, 3))) + [n_loc - 1]:
         Jr, _ = O.lkhd_sufficient_statistics(X, om[:, j], np.zeros(T))
         np.testing.assert_allclose(np.tril(J[j, :D, :D]), np.tril(Jr), rtol=RTOL, atol=0)
+
+
+def test_gram_and_h_at_the_benchmark_shape(K):
+    """cfg3 itself (N=200, B=2, T=1e5, all 200 neurons local: D = 401, 80 601 pairs, two neuron tiles of 112 -- the
+    `gram_tc_kernel<4, true>` instantiation bench.py times): J for neurons on both sides of the tile boundary and h
+    against the oracle's X^T diag(omega) X and X^T kappa (regression.py:251-260)."""
+    from pyglm_b200.kernels import pad_ldn
+    T, N, B, L = 100000, 200, 2, 100
+    D = N * B + 1
+    rng = np.random.default_rng(11)
+    Y = spikes(T, N, seed=0)
+    basis = O.cosine_basis(B, L) / L
+    Xp = design(K, Y, basis)
+    X = Xp[:, :N * B].cpu().numpy()
+    psi = rng.standard_normal((T, N)) - 2.0
+    om = np.zeros((T, pad_ldn(N)))
+    om[:, :N] = O.pg1_mean(psi) * rng.uniform(0.2, 1.8, size=(T, N))       # PG-like: positive, O(0.1), skewed
+    plan = K.gram_tc_plan(Xp, D, N, 4)
+    assert plan.geom["n_ntiles"] == 2
+    J = plan.gram(K.to_device(om))
+    kap = np.zeros((T, pad_ldn(N)))
+    kap[:, :N] = Y - 0.5
+    h = K.xt_kappa(Xp, K.to_device(kap), D, N).cpu().numpy()
+    for n in (0, 111, 112, 199):
+        Jr, hr = O.lkhd_sufficient_statistics(X, om[:, n], kap[:, n])
+        np.testing.assert_allclose(np.tril(J[n, :D, :D].cpu().numpy()), np.tril(Jr), rtol=RTOL, atol=0)
+        np.testing.assert_allclose(h[n, :D], hr, rtol=RTOL, atol=1e-9)
+    # and the FP64 DMMA kernel (the engine's checker) for one neuron of the same problem
+    J64 = K.weighted_gram(Xp, K.to_device(np.ascontiguousarray(om[:, 112:176])), D, 1).cpu().numpy()[0]
+    Jr, _ = O.lkhd_sufficient_statistics(X, om[:, 112], kap[:, 112])
+    np.testing.assert_allclose(np.tril(J64[:D, :D]), np.tril(Jr), rtol=RTOL, atol=0)
 
 
 class _MaxWith(object):
@@ -315,6 +397,14 @@ def test_gram_tc_time_slabs_sum_to_the_unsharded_integers(K, T, cut, N, B, n_loc
         assert torch.equal(plan.omax, full.omax)
         tot += plan.mma()
     assert torch.equal(tot, Jint_full)
+    tot_s = torch.zeros_like(Jint_full)
+    for lo, hi in [(0, cut), (cut, T)]:                       # and with the Z tiles built inside the kernel
+        comm = _MaxWith(full.cmax.clone())
+        plan = K.gram_tc_plan(Xp[lo:hi].contiguous(), D, n_loc, S, comm=comm, t_off=lo, stream=True)
+        comm.pending = [full.omax.clone()]
+        plan.slice_omega(om_d[lo:hi].contiguous())
+        tot_s += plan.mma()
+    assert torch.equal(tot_s, Jint_full)
     J = full.finalize(K.zeros(n_loc, full.ldx, full.ldx), Jint=tot)
     assert torch.equal(J, full.finalize(K.zeros(n_loc, full.ldx, full.ldx)))
 
@@ -395,7 +485,10 @@ def test_marginal_likelihood_kat(K, golden):
 
 
 @pytest.mark.parametrize("N,B,T,n_loc,seed", [(6, 2, 400, 6, 0), (27, 3, 3000, 5, 1), (40, 1, 2000, 7, 2),
-                                              (12, 4, 1500, 3, 3), (90, 2, 6000, 2, 4)])
+                                              (12, 4, 1500, 3, 3), (90, 2, 6000, 2, 4),
+                                              # the benchmark's shape: N = 200, B = 2 -> D = 401, active sets of ~280
+                                              # coordinates
+                                              (200, 2, 20000, 2, 5)])
 def test_spike_slab_random_vs_oracle(K, N, B, T, n_loc, seed):
     """Random problems: full regression.resample (a-scan + W draw) vs the oracle on injected draws, with
     neuron-specific, non-isotropic priors as the NIW network step produces them (models.py:232-236).  The last case
@@ -416,7 +509,7 @@ def test_spike_slab_random_vs_oracle(K, N, B, T, n_loc, seed):
         Jl, hl = O.lkhd_sufficient_statistics(X, om, Y[:, j] - 0.5)
         Js.append(Jl)
         hs.append(hl)
-        a0s.append(rng.random(N) < 0.5)
+        a0s.append(rng.random(N) < (0.7 if N >= 200 else 0.5))
         perms.append(rng.permutation(N))
         uss.append(rng.random(N))
         zs.append(rng.standard_normal(N * B + 1))
