@@ -555,10 +555,14 @@ class OracleSparseBernoulliGLM(object):
 # Restatement of the arithmetic of pyglm_b200/csrc/gram_tc.cu (OUR tensor-core formulation of
 # regression.py:251-256, not a reference function): used by the tests to check the digit planes and the int64
 # sums of the tcgen05 kernel bit for bit.  The FP64 value it approximates is lkhd_sufficient_statistics above.
-def tc_exponent(cmax):
-    """2^e > 1.02 * cmax (0 for an all-zero column)."""
-    import math
-    return 0 if not cmax > 0 else math.frexp(cmax * 1.02)[1]
+def tc_bound(cmax):
+    """The value that maps to 2^(8S) in a row's fixed-point representation: 1.02 x its largest entry (1 for an all-zero
+    row).  Not rounded to a power of two (gram_tc.cu: tc_bound)."""
+    return cmax * 1.02 if cmax > 0 else 1.0
+
+
+def tc_scale(cmax, S):
+    return 2.0 ** (8 * S) / tc_bound(cmax)
 
 
 def tc_digits_int(v, S):
@@ -601,11 +605,11 @@ def tc_rword(t):
     return x ^ (x >> np.uint64(16))
 
 
-def tc_xq(Xt, i, ex, S, t_off=0):
-    """Fixed-point column i of the design: rint(x 2^(8S - e_i) + dither(i, global bin)) as Python-int-safe uint64."""
+def tc_xq(Xt, i, bx, S, t_off=0):
+    """Fixed-point column i of the design: rint(x 2^(8S) / bx_i + dither(i, global bin)) as uint64."""
     T = Xt.shape[0]
     t = np.arange(T, dtype=np.uint64) + np.uint64(t_off)
-    v = np.rint(Xt[:, i] * 2.0 ** (8 * S - ex[i]) + tc_dither(np.full(T, i, dtype=np.uint64), t))
+    v = np.rint(Xt[:, i] * (2.0 ** (8 * S) / bx[i]) + tc_dither(np.full(T, i, dtype=np.uint64), t))
     return v.astype(np.int64).astype(np.uint64)
 
 
@@ -629,14 +633,14 @@ def tc_z_digits(Xt, i, j, ex, S, t_off=0):
 def tc_gram_reference(Xt, om, S, t_off=0, ex=None, eo=None):
     """Xt (T, D) = [X, 1] >= 0, om (T, n) > 0.  Returns (Jint (n, D(D+1)/2) int64 exact digit sums,
     J (n, D, D) float64 lower triangle) as gram_tc.cu computes them.  ex / eo: scale exponents when they come from a
-    longer recording than Xt (time slabs).  The digit dot products run as float64 matrix products: every partial sum
+    longer recording than Xt (time slabs): the rows' bounds (tc_bound of the column maxima).  The digit dot products run as float64 matrix products: every partial sum
     is an integer below 2^53, hence exact."""
     T, D = Xt.shape
     n = om.shape[1]
     assert T * 4 * 255 * 255 < 2 ** 53
-    ex = [tc_exponent(c) for c in Xt.max(0)] if ex is None else ex
-    eo = [tc_exponent(c) for c in om.max(0)] if eo is None else eo
-    od = [np.stack([tc_digits(om[:, c] * 2.0 ** (8 * S - eo[c]), S)[b] for c in range(n)], axis=1).astype(np.float64)
+    ex = [tc_bound(c) for c in Xt.max(0)] if ex is None else ex
+    eo = [tc_bound(c) for c in om.max(0)] if eo is None else eo
+    od = [np.stack([tc_digits(om[:, c] * (2.0 ** (8 * S) / eo[c]), S)[b] for c in range(n)], axis=1).astype(np.float64)
           for b in range(S)]                                              # od[b]: (T, n)
     xq = np.stack([tc_xq(Xt, i, ex, S, t_off) for i in range(D)], axis=1)  # (T, D) uint64
     rw = tc_rword(np.arange(T, dtype=np.uint64) + np.uint64(t_off))
@@ -655,5 +659,5 @@ def tc_gram_reference(Xt, om, S, t_off=0, ex=None, eo=None):
         p0 = i * (i + 1) // 2
         Jint[:, p0:p0 + i + 1] = tot.T
         for c in range(n):
-            J[c, i, :i + 1] = tot[:, c].astype(np.float64) * 2.0 ** (np.array(ex[:i + 1]) + ex[i] + eo[c] - 8 * S - 8)
+            J[c, i, :i + 1] = tot[:, c].astype(np.float64) * (((ex[i] * np.array(ex[:i + 1])) * eo[c]) * 2.0 ** (-8 * S - 8))
     return Jint, J

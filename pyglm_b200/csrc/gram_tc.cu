@@ -5,8 +5,8 @@
 //     J[(i,j), n] = sum_t Z[t,(i,j)] * omega[t,n],      Z[t,(i,j)] = X~[t,i] X~[t,j]   (i >= j)
 //
 // Both operands are written as S radix-256 digits of a fixed-point number with a power-of-two scale per row,
-//     Z[t,p]     ~ 2^(ex_i+ex_j-8S) * sum_s 256^(S-1-s) zs[s][p][t]       (scale: product of column bounds of X~)
-//     omega[t,n] ~ 2^(eo_n-8S)      * sum_s 256^(S-1-s) os[s][n][t]       (scale: column maximum of omega)
+//     Z[t,p]     ~ bx_i bx_j 2^(-8S) * sum_s 256^(S-1-s) zs[s][p][t]       (bx = 1.02 x column maximum of X~)
+//     omega[t,n] ~ bo_n 2^(-8S)      * sum_s 256^(S-1-s) os[s][n][t]       (bo = 1.02 x column maximum of omega)
 // digit 0 unsigned in [0,255] (all operands are >= 0 on this path), digits 1.. signed in [-128,127].  Z is formed in
 // INTEGER arithmetic from the fixed-point design xq[i][t] = rint(X~[t,i] 2^(8S-ex_i) + dither(i,t)):
 //     Z_fix[(i,j)][t] = (xq_i xq_j + rnd(t)) >> 8S             rnd = bin-keyed dither of the dropped low half
@@ -43,13 +43,12 @@ constexpr long long TC_SPIN_LIMIT = 4000000000LL;   // cycles; a wait this long 
 
 __host__ __device__ inline int tc_nt_max(int S) { return (512 / S) / 16 * 16; }   // TMEM: S accumulators x NT columns
 
-// power-of-two scale exponent: 2^e > 1.02 * cmax  (digit 0 then stays <= 252)
-__host__ __device__ inline int tc_exponent(double cmax) {
-    if (!(cmax > 0.0)) return 0;
-    int e;
-    frexp(cmax * 1.02, &e);
-    return e;
-}
+// Fixed-point scale of a row whose largest entry is cmax: the value 1.02 * cmax ("bound") maps to 2^(8S), so digit 0
+// stays <= 251.  The scale is NOT rounded to a power of two: that would leave between zero and one bit of every operand
+// unused, and because the accuracy of four digits is set by the dropped order-4 digit products -- a fixed absolute
+// error per time bin -- the three wasted half bits cost a factor 3-7 in the worst relative deviation (measured).
+__host__ __device__ inline double tc_bound(double cmax) { return (cmax > 0.0) ? cmax * 1.02 : 1.0; }
+__host__ __device__ inline double tc_scale(double cmax, int S) { return ldexp(1.0, 8 * S) / tc_bound(cmax); }
 
 // 32-bit mixer (lowbias32) behind the product dither
 __host__ __device__ inline uint32_t tc_hash32(uint32_t x) {
@@ -941,10 +940,11 @@ template <int S>
 __device__ __forceinline__ void tc_digits(double scaled, unsigned (&d)[S]) {
     tc_digits_int<S>(__double2ll_rn(scaled), d);
 }
-// fixed-point design entry: rint(x 2^(8S - e) + dither(column, global bin))  (< 2^(8S) / 1.02)
+// fixed-point design entry: rint(x * scale + dither(column, global bin))  (<= 2^(8S) / 1.02)
 template <int S>
-__device__ __forceinline__ unsigned long long tc_xq(double x, int e, int col, unsigned long long t_global) {
-    return (unsigned long long)__double2ll_rn(x * ldexp(1.0, 8 * S - e) + tc_dither((unsigned long long)col, t_global));
+__device__ __forceinline__ unsigned long long tc_xq(double x, double scale, int col, unsigned long long t_global) {
+    // separately rounded product and sum (no FMA contraction): the numpy emulation in the tests must give the same bits
+    return (unsigned long long)__double2ll_rn(__dadd_rn(__dmul_rn(x, scale), tc_dither((unsigned long long)col, t_global)));
 }
 // Z_fix = (xq_i xq_j + rnd) >> 8S with rnd uniform over the dropped 8S bits
 template <int S>
@@ -968,7 +968,7 @@ zslice_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const 
     const int tid = threadIdx.x;
     const int jl = tid >> 3, tq = tid & 7;
     const int j = j0 + jl;
-    const int ei = tc_exponent(cmax[i]);
+    const double si = tc_scale(cmax[i], S);
     const long long p = (long long)i * (i + 1) / 2 + j;
     for (long long tb = (long long)blockIdx.z * 128; tb < Tpad; tb += (long long)gridDim.z * 128) {
         __syncthreads();
@@ -976,10 +976,10 @@ zslice_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, const 
             const int r = x >> 5, c = x & 31;
             const long long t = tb + r;
             xs[c][r] = (t < T && j0 + c <= i)
-                           ? tc_xq<S>(Xp[t * ldx + j0 + c], tc_exponent(cmax[j0 + c]), j0 + c, (unsigned long long)(t_off + t)) : 0ull;
+                           ? tc_xq<S>(Xp[t * ldx + j0 + c], tc_scale(cmax[j0 + c], S), j0 + c, (unsigned long long)(t_off + t)) : 0ull;
         }
         if (tid < 128) {
-            xi[tid] = (tb + tid < T) ? tc_xq<S>(Xp[(tb + tid) * ldx + i], ei, i, (unsigned long long)(t_off + tb + tid)) : 0ull;
+            xi[tid] = (tb + tid < T) ? tc_xq<S>(Xp[(tb + tid) * ldx + i], si, i, (unsigned long long)(t_off + tb + tid)) : 0ull;
             rws[tid] = tc_rword((unsigned long long)(t_off + tb + tid));
         }
         __syncthreads();
@@ -1023,7 +1023,7 @@ quantize_kernel(const double* __restrict__ Xp, int ldx, long long T, int D, cons
         const long long t = tb + r;
         uint32_t v = 0u;
         if (t < T && c0 + c < D)
-            v = (uint32_t)tc_xq<4>(Xp[t * ldx + c0 + c], tc_exponent(cmax[c0 + c]), c0 + c, (unsigned long long)(t_off + t));
+            v = (uint32_t)tc_xq<4>(Xp[t * ldx + c0 + c], tc_scale(cmax[c0 + c], 4), c0 + c, (unsigned long long)(t_off + t));
         tile[c][r] = v;
     }
     __syncthreads();
@@ -1053,7 +1053,7 @@ oslice_kernel(const double* __restrict__ Om, int ldo, long long T, int n_valid, 
     const int nl = tid >> 3, tq = tid & 7;
     const int n = n0 + nl;
     if (n >= n_valid || tb + tq * 16 >= Tpad) return;
-    const double scale = ldexp(1.0, 8 * S - tc_exponent(omax[n]));
+    const double scale = tc_scale(omax[n], S);
     unsigned pk[S][4];
 #pragma unroll
     for (int s = 0; s < S; ++s) pk[s][0] = pk[s][1] = pk[s][2] = pk[s][3] = 0u;
@@ -1074,8 +1074,8 @@ oslice_kernel(const double* __restrict__ Om, int ldo, long long T, int n_valid, 
     }
 }
 
-// J[n][i][j] (i >= j) = Jint[n][pair(i,j)] * 2^(ex_i + ex_j + eo_n - 8 S - 8): the operands carry 2^(8S) each and the
-// order-g accumulators were weighted 256^(S-1-g) instead of 256^(2S-2-g).
+// J[n][i][j] (i >= j) = Jint[n][pair(i,j)] * bound_i bound_j bound_n 2^(-8 S - 8): every operand carries 2^(8S) / bound,
+// Z_fix dropped 2^(8S), and the order-g accumulators were weighted 256^(S-1-g) instead of 256^(2S-2-g).
 __global__ void __launch_bounds__(256)
 gram_tc_finalize_kernel(const long long* __restrict__ Jint, long long ldjint, const double* __restrict__ cmax,
                         const double* __restrict__ omax, int D, int S, double* __restrict__ J, long long stride_n, int ldj) {
@@ -1084,8 +1084,8 @@ gram_tc_finalize_kernel(const long long* __restrict__ Jint, long long ldjint, co
     const int j = blockIdx.x * 256 + threadIdx.x;
     if (j > i) return;
     const long long p = (long long)i * (i + 1) / 2 + j;
-    const int e = tc_exponent(cmax[i]) + tc_exponent(cmax[j]) + tc_exponent(omax[n]) - 8 * S - 8;
-    J[(long long)n * stride_n + (long long)i * ldj + j] = ldexp((double)Jint[(long long)n * ldjint + p], e);
+    const double unit = ldexp((tc_bound(cmax[i]) * tc_bound(cmax[j])) * tc_bound(omax[n]), -8 * S - 8);
+    J[(long long)n * stride_n + (long long)i * ldj + j] = (double)Jint[(long long)n * ldjint + p] * unit;
 }
 
 // ------------------------------------------------------------------------------------------ host side

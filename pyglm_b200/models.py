@@ -163,35 +163,39 @@ class NonlinearAutoregressiveModel(object):
         return self.adjacency, self.weights, self.biases
 
     # ------------------------------------------------------------------ data (models.py:66-80)
-    def add_data(self, data, X=None, host_X=True):
+    def add_data(self, data, X=None, host_X=True, slab=None):
         """Append a (T, N) spike matrix.  X (T, N, B) may be supplied; otherwise it is the causal convolution of
         `data` with the basis, computed on the GPU.  host_X=False keeps X in HBM only (data_list then holds a
-        DeviceDesign handle): use it for recordings whose X should not be mirrored in host RAM."""
+        DeviceDesign handle): use it for recordings whose X should not be mirrored in host RAM.
+
+        slab=(t0, T_total), time-sharded runs only: `data` holds the global bins [t0, t0 + len(data)) of a recording of
+        T_total bins -- this rank's slab plus the L bins before it (the filter's history) -- instead of the whole
+        recording, so that a 1e7-bin recording never has to exist in one process."""
         N, B = self.N, self.B
         assert isinstance(data, np.ndarray) and data.ndim == 2 and data.shape[1] == self.N
-        T = data.shape[0]
+        t0, T = (0, data.shape[0]) if slab is None else (int(slab[0]), int(slab[1]))
         if X is None:
             lo, hi = self._time_slab(T)
             if host_X and (lo, hi) != (0, T):
                 raise ValueError("time-sharded add_data needs host_X=False (each rank holds only its slab)")
-            if lo > 0:
-                # filter halo: the L bins before the slab (zero history only at the true start)
-                L = self.basis.shape[0]
-                h0 = max(0, lo - L)
-                ds_full = self.engine.make_dataset(data[h0:hi], basis=self.basis, t_off=h0, T_global=T)
-                ds_full.Xp = ds_full.Xp[lo - h0:].contiguous()
-                ds_full.Y = ds_full.Y[lo - h0:].contiguous()
-                ds_full.T, ds_full.t_off = hi - lo, lo
-                ds = ds_full
-            else:
-                ds = self.engine.make_dataset(data[lo:hi], basis=self.basis, t_off=lo, T_global=T)
+            # filter halo: the L bins before the slab (zero history only at the true start)
+            L = self.basis.shape[0]
+            h0 = max(0, lo - L)
+            if not (t0 <= h0 and hi <= t0 + data.shape[0]):
+                raise ValueError("add_data(slab=...): bins [%d, %d) needed, [%d, %d) given"
+                                 % (h0, hi, t0, t0 + data.shape[0]))
+            ds = self.engine.make_dataset(data[h0 - t0:hi - t0], basis=self.basis, t_off=h0, T_global=T)
+            if lo > h0:
+                ds.Xp = ds.Xp[lo - h0:].contiguous()
+                ds.Y = ds.Y[lo - h0:].contiguous()
+                ds.T, ds.t_off = hi - lo, lo
             if host_X:
                 X = np.asarray(DeviceDesign(ds, N, B))
             else:
                 X = DeviceDesign(ds, N, B)
             self._dev[(id(X), id(data))] = (X, data, ds)
         else:
-            assert X.shape == (T, N, B)
+            assert slab is None and X.shape == (T, N, B)
         self.data_list.append((X, data))
 
     # ------------------------------------------------------------------ scoring (models.py:82-96)

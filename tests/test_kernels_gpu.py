@@ -266,7 +266,7 @@ def test_gram_tc_integer_sums_are_exact(K, T, N, B, n_loc, S):
     om_d = K.to_device(om)
     plan.slice_omega(om_d)
     Zs = plan.Zs.cpu().numpy()
-    ex = [O.tc_exponent(c) for c in Xt.max(0)]
+    ex = [O.tc_bound(c) for c in Xt.max(0)]
     for (i, j) in [(0, 0), (D - 1, 0), (D - 1, D - 1), (D // 2, D // 3)]:
         zd = O.tc_z_digits(Xt, i, j, ex, S)
         for s in range(S):

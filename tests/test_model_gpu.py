@@ -395,9 +395,9 @@ def test_learned_adjacency_priors_drive_the_scan(prior):
 def test_engine_moves_to_five_digits_when_four_miss_the_tolerance():
     """The accuracy of the integer-digit Gram depends on the data (how much of the fixed-point range the typical
     entry uses), so the engine measures it per data set against the FP64 kernel on the first sweep's own omega and
-    keeps four digits only within TC_ACCEPT; otherwise five digits (resident planes), otherwise FP64.  This recording
-    (short basis, T = 7e4) is one where four digits miss 5e-10 on a few entries: whatever the engine settles on must
-    meet the tolerance, and the spot check of later sweeps must agree."""
+    keeps four digits only within TC_ACCEPT; otherwise five digits (resident planes), otherwise FP64.  Four digits
+    reach ~4e-10 on this recording (short basis, T = 7e4): with the acceptance threshold lowered to 1e-10 the engine
+    has to settle on five digits, meet the threshold there, and the spot checks of later sweeps must agree."""
     from pyglm_b200.models import SparseBernoulliGLM
     from pyglm_b200.utils.basis import cosine_basis
     N, B, L, T = 40, 2, 20, 70000
@@ -406,13 +406,20 @@ def test_engine_moves_to_five_digits_when_four_miss_the_tolerance():
     m = SparseBernoulliGLM(N, basis=cosine_basis(B, L) / L, regression_kwargs=dict(S_w=10.0, mu_b=-2.), seed=5, gram="tc")
     m.add_data(Y, host_X=False)
     eng = m.engine
+    eng.TC_ACCEPT = 1e-10
     eng.TC_RECHECK_EVERY = 2
     for _ in range(5):
         m.resample_model()
     eng._tc_poll(force=True)
     ds = m._device_datasets()[0]
     plan = ds.buffers[("tc_plan", N)]
-    assert plan is not None and plan.verified
+    assert plan is not None and plan.verified and plan.S == 5 and not plan.stream
     assert plan.max_rel_dev <= eng.TC_ACCEPT
     assert plan.checks >= 1 and plan.max_rel_dev_spot is not None and plan.max_rel_dev_spot <= eng.TC_ACCEPT
     assert np.isfinite(m.log_likelihood())
+    # and with the default threshold four digits, built inside the kernel, are kept
+    m2 = SparseBernoulliGLM(N, basis=cosine_basis(B, L) / L, regression_kwargs=dict(S_w=10.0, mu_b=-2.), seed=5, gram="tc")
+    m2.add_data(Y, host_X=False)
+    m2.resample_model()
+    plan2 = m2._device_datasets()[0].buffers[("tc_plan", N)]
+    assert plan2.S == 4 and plan2.stream and plan2.max_rel_dev <= m2.engine.TC_ACCEPT
