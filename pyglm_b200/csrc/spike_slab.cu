@@ -1311,6 +1311,47 @@ struct Blocked {
     }
 };
 
+// DRAW, blocked: [W_S; b] = L^-T (L^-1 hp + z), Jp_SS = L L^T in ascending coordinate order with the bias last
+// (np.ix_(mask, mask), regression.py:350-353; sample_gaussian(J=, h=), :334).  On return c.cidx / c.mu / c.xs / c.K
+// describe the draw (value of coordinate cidx[k] = mu[k] + xs[k]) and ml holds _marginal_likelihood of the final a
+// (the cprior terms are added by thread 0 only).  false: Jp_SS is not positive definite.
+template <int B, int NTHR, int C>
+__device__ __forceinline__ bool blocked_draw(FastCtx<B, NTHR, C>& c, Blocked<NTHR, C>& blk, const unsigned char* a,
+                                             const double* zc, const double* cprior, bool want_ml, int* ksh, double& ml) {
+    const int N = c.N, D = c.D, tid = c.tid;
+    csync<C>();
+    if (tid == 0) {
+        int K = 0;
+        for (int m = 0; m < N; ++m)
+            if (a[m])
+                for (int b = 0; b < B; ++b) c.cidx[K++] = m * B + b;
+        c.cidx[K++] = D - 1;
+        *ksh = K;
+    }
+    csync<C>();
+    const int K = *ksh;
+    for (int i = c.warp; i < K; i += NTHR / 32) {
+        const int ci = c.cidx[i];
+        for (int j = c.lane; j <= i; j += 32) c.P[(size_t)i * c.ldp + j] = c.Jp(ci, c.cidx[j]);
+    }
+    for (int j = tid; j < K; j += NTHR) c.mu[j] = c.hp(c.cidx[j]);
+    csync<C>();
+    double half_logdet = 0.0;
+    if (!blk.cholesky(K, c.mu, &half_logdet)) return false;
+    double quad = 0.0;                                    // every thread, same order: |L^-1 hp|^2
+    for (int j = 0; j < K; ++j) quad += c.mu[j] * c.mu[j];
+    for (int j = tid; j < K; j += NTHR) c.xs[j] = c.mu[j] + zc[c.cidx[j]];
+    csync<C>();
+    blk.backsolve(K, c.xs, c.tb);                         // xs = L^-T (L^-1 hp + z) = Jp^-1 hp + L^-T z
+    for (int j = tid; j < K; j += NTHR) c.mu[j] = 0.0;
+    ml = -half_logdet + 0.5 * quad + 0.5 * log(c.J0b) - 0.5 * c.h0b * c.h0b / c.J0b;
+    if (want_ml && tid == 0)
+        for (int m = 0; m < N; ++m)
+            if (a[m]) ml += cprior[m];
+    c.K = K;
+    return true;
+}
+
 template <int B, int NTHR>
 size_t fast_smem_bytes(int N) {
     const int D = N * B + 1, Dpad = (D + 1) & ~1;
@@ -1511,40 +1552,7 @@ spike_slab_fast_kernel(SpikeSlabArgs A) {
         else if (draw && is_bias) phase = PH_DONE;
     }
     if (BLK && !fail && phase == PH_DRAW) {
-        // DRAW, blocked: ascending coordinate order with the bias last (np.ix_(mask, mask), regression.py:350-353)
-        csync<C>();
-        if (tid == 0) {
-            int K = 0;
-            for (int m = 0; m < N; ++m)
-                if (a[m])
-                    for (int b = 0; b < B; ++b) c.cidx[K++] = m * B + b;
-            c.cidx[K++] = D - 1;
-            *ksh = K;
-        }
-        csync<C>();
-        const int K = *ksh;
-        for (int i = c.warp; i < K; i += NTHR / 32) {
-            const int ci = c.cidx[i];
-            for (int j = c.lane; j <= i; j += 32) c.P[(size_t)i * c.ldp + j] = c.Jp(ci, c.cidx[j]);
-        }
-        for (int j = tid; j < K; j += NTHR) c.mu[j] = c.hp(c.cidx[j]);
-        csync<C>();
-        double half_logdet = 0.0;
-        if (!blk.cholesky(K, c.mu, &half_logdet)) {
-            fail = 1;
-        } else {
-            double quad = 0.0;                            // every thread, same order: |L^-1 hp|^2
-            for (int j = 0; j < K; ++j) quad += c.mu[j] * c.mu[j];
-            for (int j = tid; j < K; j += NTHR) c.xs[j] = c.mu[j] + zc[c.cidx[j]];
-            csync<C>();
-            blk.backsolve(K, c.xs, c.tb);                 // xs = L^-T (L^-1 hp + z) = Jp^-1 hp + L^-T z
-            for (int j = tid; j < K; j += NTHR) c.mu[j] = 0.0;
-            ml = -half_logdet + 0.5 * quad + 0.5 * log(c.J0b) - 0.5 * c.h0b * c.h0b / c.J0b;
-            if (A.ml && tid == 0)
-                for (int m = 0; m < N; ++m)
-                    if (a[m]) ml += cprior[m];
-            c.K = K;
-        }
+        if (!blocked_draw<B, NTHR, C>(c, blk, a, zc, cprior, A.ml != nullptr, ksh, ml)) fail = 1;
     }
     csync<C>();
     double* Wn = A.W + (size_t)ln * N * B;
