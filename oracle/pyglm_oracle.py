@@ -83,6 +83,45 @@ def pg1_var(psi):
     return np.where(np.abs(psi) < 1e-3, 1.0 / 24.0, v)
 
 
+def jstar_cdf(x, z, form="auto", terms=200):
+    """P(J*(1, z) <= x), the law Devroye's sampler draws from (PG(1, psi) = J*(1, |psi|/2) / 4; Polson, Scott &
+    Windle 2013, eqs. (12)-(14)).  Independent of the sampler: the density is cosh(z) exp(-x z^2/2) sum_n (-1)^n a_n(x)
+    and each piece of the alternating series integrates in closed form.
+      left  (fast for small x): a_n(x) = 2 c/sqrt(2 pi x^3) exp(-c^2/(2x)), c = 2n+1, i.e. twice the first-passage
+            density of level c; with the tilt exp(-z^2 x/2) the integral is exp(-cz) P(tau_c <= x) for a Brownian
+            motion with drift z:   2 cosh(z) sum (-1)^n [ e^{-cz} Phi((zx-c)/sqrt x) + e^{cz} Phi(-(zx+c)/sqrt x) ]
+      right (fast for large x): a_n(x) = pi(n+1/2) exp(-(n+1/2)^2 pi^2 x/2); with lam_n = z^2/2 + (n+1/2)^2 pi^2/2
+            and sum (-1)^n pi(n+1/2)/lam_n = 1/cosh(z):   1 - cosh(z) sum (-1)^n pi(n+1/2) exp(-lam_n x)/lam_n
+    form="auto" switches at the sampler's truncation point 0.64; tests check that the two forms agree there."""
+    from scipy.special import log_ndtr
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    z = abs(float(z))
+    n = np.arange(terms, dtype=np.float64)[:, None]
+    sgn = np.where(n % 2 == 0, 1.0, -1.0)
+    xs = np.maximum(x[None, :], 1e-300)
+    out = np.empty_like(x)
+    left = (x <= 0.64) if form == "auto" else np.full(x.shape, form == "left")
+    if left.any():
+        c = 2.0 * n + 1.0
+        xl = xs[:, left]
+        lcz = np.log(np.cosh(z)) if z < 300 else z - np.log(2.0)
+        t1 = np.exp(np.minimum(lcz - c * z + log_ndtr((z * xl - c) / np.sqrt(xl)), 700.0))
+        t2 = np.exp(np.minimum(lcz + c * z + log_ndtr(-(z * xl + c) / np.sqrt(xl)), 700.0))
+        out[left] = 2.0 * np.sum(sgn * (t1 + t2), axis=0)
+    if (~left).any():
+        lam = 0.5 * z * z + 0.5 * (n + 0.5) ** 2 * np.pi ** 2
+        xr = xs[:, ~left]
+        lcz = np.log(np.cosh(z)) if z < 300 else z - np.log(2.0)
+        # cosh(z) exp(-lam x) stays finite: lam x >= z^2 x / 2 and x > 0.64 only matters while z is moderate
+        out[~left] = 1.0 - np.sum(sgn * np.pi * (n + 0.5) * np.exp(lcz - lam * xr) / lam, axis=0)
+    return np.clip(np.where(x <= 0, 0.0, out), 0.0, 1.0)
+
+
+def pg1_cdf(w, psi):
+    """P(PG(1, psi) <= w) for scalar psi (regression.py:496-508 draws omega_t from this law)."""
+    return jstar_cdf(4.0 * np.asarray(w, dtype=np.float64), 0.5 * abs(float(psi)))
+
+
 # --------------------------------------------------------------------------- (1) filter build
 def cosine_basis(B, L=100, orth=False, norm=True, n_eye=0, a=1.0 / 120, b=0.5):
     """Raised-cosine bumps on a log-time axis.  Follows pyglm/utils/basis.py:61-106."""

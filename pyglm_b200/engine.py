@@ -255,6 +255,10 @@ class GibbsEngine(object):
             if plan.max_rel_dev <= self.TC_ACCEPT:
                 plan.verified = True
                 break
+            import warnings
+            warnings.warn("tensor-core Gram with %d digits deviates from the FP64 kernel by %.2e (> %.1e) on the first "
+                          "sweep: trying %s" % (plan.S, plan.max_rel_dev, self.TC_ACCEPT,
+                                                "5 digits" if plan.S < 5 else "the FP64 kernel"))
             digits = plan.S + 1
             ds.buffers[key] = plan = None
             torch.cuda.empty_cache()

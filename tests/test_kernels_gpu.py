@@ -204,6 +204,44 @@ def test_pg_moments(K, z):
     assert abs(x.var() - v) < 0.02 * v
 
 
+@pytest.mark.parametrize("variant", ["1", "2"])
+@pytest.mark.parametrize("z", [0.0, 0.5, 2.0, 5.0, 12.0])
+def test_pg_draws_follow_the_pg_law(K, z, variant, monkeypatch):
+    """Kolmogorov-Smirnov: GPU draws (one-pass and branch-compacted kernels) against the closed-form CDF of PG(1, psi)
+    (oracle.pg1_cdf, pinned in tests/test_oracle_pg.py), and two-sample against the oracle's C sampler on another
+    seed (regression.py:496-508; SURVEY 8c: "KS against the oracle sampler per psi bucket")."""
+    from scipy import stats
+    from pyglm_b200.kernels import pad_ldn
+    monkeypatch.setenv("PYGLM_PG_VARIANT", variant)
+    T = 200000
+    psi = K.zeros(T, pad_ldn(1))
+    psi[:, 0] = -z                                            # the sampler must take |psi|
+    om = K.zeros(T, pad_ldn(1))
+    K.pg_draw(psi, 1, om, 1234 + int(10 * z), 3, 0, 0, 1)
+    x = om[:, 0].cpu().numpy()
+    assert stats.kstest(x, lambda v: O.pg1_cdf(v, z)).pvalue > 1e-3
+    y = O.pg1_draw(np.full(T, z), seed=99, call_id=1, rng_kind=1)
+    assert stats.ks_2samp(x, y).pvalue > 1e-3
+
+
+def test_pg_draws_probability_integral_transform_at_benchmark_psi(K):
+    """psi ~ N(-2, 1) as in the benchmark's chains, many distinct values in one launch (every proposal branch, both
+    list ends of the two-pass sampler): u = F(omega; psi) must be uniform."""
+    from scipy import stats
+    from pyglm_b200.kernels import pad_ldn
+    rng = np.random.default_rng(8)
+    vals = np.round(rng.standard_normal(300) - 2.0, 2)
+    vals[:4] = [0.0, 7.5, -9.0, 3.0]
+    rep, n = 200, 3
+    psi = np.zeros((len(vals) * rep, pad_ldn(n)))
+    psi[:, :n] = np.repeat(vals, rep)[:, None]
+    om = K.zeros(*psi.shape)
+    K.pg_draw(K.to_device(psi), n, om, 77, 5, 0, 0, n)
+    x = om[:, :n].cpu().numpy().reshape(len(vals), rep * n)
+    u = np.concatenate([O.pg1_cdf(x[i], v) for i, v in enumerate(vals)])
+    assert stats.kstest(u, "uniform").pvalue > 1e-3
+
+
 # ----------------------------------------------------------------------------- (3) weighted Gram, h
 @pytest.mark.parametrize("T,N,B,n_loc,nslabs", [(50, 3, 2, 3, None), (2000, 27, 3, 27, None), (2000, 27, 3, 27, 1),
                                                 (3000, 40, 2, 13, 3), (1500, 9, 1, 9, None), (4100, 20, 2, 70, 2)])
