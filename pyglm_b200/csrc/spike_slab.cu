@@ -24,39 +24,14 @@
 //
 // Randomness (permutation, uniforms, normals) is read from device buffers so tests can inject the reference's
 // own draws; in production those buffers are filled by pyglm_scan_randomness (Philox, below).
-#include "common.cuh"
+#include "spike_slab_common.cuh"
 #include <cooperative_groups.h>
 #include "philox.cuh"
 #include <stdlib.h>
 
+using namespace pyglm_ss;
+
 namespace {
-
-constexpr int SS_BMAX = 16;
-
-struct SpikeSlabArgs {
-    int N, B, D, n_loc;
-    const double* J; long long stride_n; int ldj;     // likelihood J (lower triangle valid), per local neuron
-    const double* h; int ldh;                          // likelihood h
-    const double* J0w;                                 // (n_loc, N, B, B) prior precision blocks
-    const double* h0w;                                 // (n_loc, N, B)
-    const double* J0b; const double* h0b;              // (n_loc,)
-    const double* cprior;                              // (n_loc, N)   1/2 log|J0_m| - 1/2 h0_m^T J0_m^-1 h0_m
-    const double* logit_rho;                           // (n_loc, N)   log rho - log(1 - rho)
-    const int* perm;                                   // (n_loc, N)
-    const double* us;                                  // (n_loc, N)
-    const double* z;                                   // (n_loc, ldz) standard normals keyed by coordinate
-    int ldz;
-    const unsigned char* do_scan;                      // (n_loc,) 0 -> keep a as given (deterministic sparsity)
-    unsigned char* a;                                  // (n_loc, N) in/out
-    double* W;                                         // (n_loc, N, B) out
-    double* bias;                                      // (n_loc,) out
-    double* P;                                         // workspace (n_loc, D, D)
-    double* logodds;                                   // optional (n_loc, N): log-odds per scan step
-    double* ml;                                        // optional (n_loc,): marginal likelihood of the final a
-    int* status;                                       // (n_loc,) 0 ok, 1 = a Schur complement lost positive definiteness
-    int debug;                                         // PYGLM_SS_DEBUG=1: CTA 0 prints its cycles per phase (profiling aid)
-    int la_G;                                          // slots of the scan's lookahead table (0 = off), set by the launcher
-};
 
 template <int SS_THREADS>
 struct Ctx {
@@ -480,87 +455,6 @@ spike_slab_kernel(SpikeSlabArgs A) {
 //   * passes over P keep 16 loads per lane in flight (4 rows x 4 column chunks): P lives in L2 (K x K doubles do
 //     not fit in shared memory), so memory-level parallelism sets the time of a pass;
 //   * t G (the scaled border) is recomputed per row from registers in the rank update: no staging pass.
-template <int B>
-struct SmallSolve {
-    double L[B][B], il[B], y[B];      // Cholesky factor, 1/diag, L^-1 r
-    double G[B][B], gr[B], xm[B];     // (L L^T)^-1, G r, L^-T z
-    double dpost;
-};
-
-// Cholesky of the lower triangle of S (BS x BS) and the quadratic form: dpost = sgn 1/2 log|S| + 1/2 r^T S^-1 r
-// (NaN when S is not positive definite).
-template <int B, int BS>
-__device__ __forceinline__ void small_factor(SmallSolve<B>& w, const double (&S)[B][B], const double (&r)[B], double sgn) {
-    double det = 1.0, q = 0.0;
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < BS; ++j) {
-        double d = S[j][j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) d -= w.L[j][k] * w.L[j][k];
-        ok = ok && (d > 0.0);
-        det *= d;
-        w.il[j] = rsqrt(d);
-        w.L[j][j] = d * w.il[j];
-#pragma unroll
-        for (int i = j + 1; i < BS; ++i) {
-            double v = S[i][j];
-#pragma unroll
-            for (int k = 0; k < j; ++k) v -= w.L[i][k] * w.L[j][k];
-            w.L[i][j] = v * w.il[j];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < BS; ++i) {                        // y = L^-1 r
-        double v = r[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) v -= w.L[i][k] * w.y[k];
-        w.y[i] = v * w.il[i];
-        q += w.y[i] * w.y[i];
-    }
-    w.dpost = ok ? sgn * 0.5 * log(det) + 0.5 * q : nan("");
-}
-
-// What a committed step needs on top of small_factor: G = S^-1, gr = G r, and xm = L^-T z for the draws.
-template <int B, int BS>
-__device__ __forceinline__ void small_finish(SmallSolve<B>& w, const double (&r)[B], const double* zc, int coord0) {
-#pragma unroll
-    for (int c = 0; c < BS; ++c) {
-        double u[BS];
-#pragma unroll
-        for (int i = 0; i < BS; ++i) {
-            double v = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < i; ++k) v -= w.L[i][k] * u[k];
-            u[i] = v * w.il[i];
-        }
-#pragma unroll
-        for (int i = BS - 1; i >= 0; --i) {
-            double v = u[i];
-#pragma unroll
-            for (int k = i + 1; k < BS; ++k) v -= w.L[k][i] * w.G[k][c];
-            w.G[i][c] = v * w.il[i];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < BS; ++i) {
-        double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < BS; ++k) v += w.G[i][k] * r[k];
-        w.gr[i] = v;
-        w.xm[i] = 0.0;
-    }
-    if (zc) {
-#pragma unroll
-        for (int i = BS - 1; i >= 0; --i) {               // xm = L^-T z_m
-            double v = zc[coord0 + i];
-#pragma unroll
-            for (int k = i + 1; k < BS; ++k) v -= w.L[k][i] * w.xm[k];
-            w.xm[i] = v * w.il[i];
-        }
-    }
-}
-
 // Cluster variant (C = 2): the C CTAs of a cluster work on ONE neuron.  Both execute the same control flow on their own
 // copies of the small state (mu, cidx, panels ...); the K x K passes over P -- t = P c, the rank update, the trailing
 // updates of the blocked factorisations -- are split by row batches, the rows of t and the per-warp partial sums of an
@@ -1708,9 +1602,19 @@ extern "C" int pyglm_spike_slab_update(int N, int B, int n_loc,
     size_t smem = ((size_t)2 * Dpad + (size_t)3 * Dpad * B + 2 * SS_BMAX * SS_BMAX + 3 * SS_BMAX + 8) * sizeof(double)
                 + ((size_t)Dpad + N) * sizeof(int);
     PYGLM_CHECK_ARG(smem <= 227 * 1024, "pyglm_spike_slab_update: N*B=%d too large for the shared-memory state (%zu bytes)", N * B, smem);
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("PYGLM_SS_VARIANT"); variant = e ? atoi(e) : 0; }
-    if (B <= 4 && variant < 10) {                        // variant >= 10: force the generic kernel (tests, B > 4)
+    const char* venv = getenv("PYGLM_SS_VARIANT");         // read per call: tests switch kernels inside one process
+    const int variant = venv ? atoi(venv) : 0;
+    // Cluster kernel with P in distributed shared memory (spike_slab_dsm.cu): PYGLM_SS_VARIANT=82 / 84 / 88 force it
+    // with 2 / 4 / 8 CTAs per neuron, 80 lets it pick the cluster size; by default it runs when it applies and the
+    // neurons would leave SMs idle (spike_slab_dsm_preferred); 1 = never.
+    if (B <= 4 && (variant == 80 || variant == 82 || variant == 84 || variant == 88 ||
+                   (variant == 0 && spike_slab_dsm_preferred(A)))) {
+        const int rc = spike_slab_dsm_launch(A, variant >= 80 ? variant - 80 : 0, stream);
+        if (rc != PYGLM_ERR_UNSUPPORTED) return rc;
+        PYGLM_CHECK_ARG(variant == 0, "pyglm_spike_slab_update: PYGLM_SS_VARIANT=%d: the state of a neuron (N*B=%d) does not "
+                        "fit the shared memory of such a cluster", variant, N * B);
+    }
+    if (B <= 4 && (variant < 10 || variant >= 80)) {     // variant 10..79: force the generic kernel (tests, B > 4)
         switch (B) {
             case 1: return launch_fast_variant<1>(A, variant, stream);
             case 2: return launch_fast_variant<2>(A, variant, stream);
