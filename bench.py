@@ -352,10 +352,12 @@ def main():
     hyp = model._stacked_hypers()
     barrier()
     eng.profile = {}
+    coll0 = eng.comm.collective_calls
     ev0.record()
     for _ in range(steps):
         A, W, b = eng.sweep([ds], A, W, b, hyp)
     ev1.record()
+    coll = (eng.comm.collective_calls - coll0) / float(steps)
     barrier()
     dev_ms = ev0.elapsed_time(ev1) / steps
     kern_ms = eng.phase_ms()
@@ -409,8 +411,16 @@ def main():
         if eng.shard == "time" and world > 1:
             par = ("time-sharded psi/PG/Gram + reduce-scatter of the Gram partials (%s), neuron-sharded scan + "
                    "all-gather of (a, W, b), x%d" % ("exact int64" if tc else "FP64", world))
+            if eng.peer is not None:
+                par += ("; exchanges by our own kernels over peer-mapped memory (reduce-scatter fused into the Gram "
+                        "finalize pass, state rows pushed over NVLink), %.2f torch.distributed collectives per sweep" % coll)
+            else:
+                par += "; NCCL collectives (%.2f per sweep)" % coll
         else:
             par = "%s-sharded x%d" % (eng.shard, world)
+            if world > 1:
+                par += ("; state rows pushed over NVLink by our own kernel, %.2f torch.distributed collectives per sweep"
+                        % coll) if eng.peer is not None else "; NCCL all-gather (%.2f collectives per sweep)" % coll
         resident = (", Z digit planes %.1f GB" % (plan.Zs.numel() / 1e9)) if (tc and not plan.stream) else ""
         line = dict(
             metric="gibbs_sweeps_per_sec", value=1e3 / dev_ms, unit="sweeps/s", n_gpus=world, steps=steps,

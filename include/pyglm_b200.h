@@ -119,6 +119,17 @@ int pyglm_gram_tc_mma_probe(const unsigned char* Zs, const unsigned char* Os, in
                             long long* Jint, long long ldjint, pyglm_stream_t stream);
 int pyglm_gram_tc_finalize(const long long* Jint, long long ldjint, const double* cmax, const double* omax,
                            int D, int n_valid, int S, double* J, long long stride_n, int ldj, pyglm_stream_t stream);
+/* time-sharded runs: the exact int64 reduce-scatter of the slabs' partial sums fused into the finalize pass.  peers is a
+ * DEVICE array of `world` base pointers to the ranks' Jint buffers (peer-mapped / symmetric memory, row pitch ldjint);
+ * rows [row_off, row_off + n_valid) of every buffer are added and scaled into this rank's J.  Stands for the
+ * reduce-scatter SURVEY 8(e) places after regression.py:251-256 on a time-sharded recording. */
+int pyglm_gram_tc_finalize_peers(const long long* const* peers /*[device]*/, int world, long long row_off, long long ldjint,
+                                 const double* cmax, const double* omax, int D, int n_valid, int S, double* J,
+                                 long long stride_n, int ldj, pyglm_stream_t stream);
+/* the all-gather of the new (a, W, b) rows (models.py:169-171) as NVLink stores: nbytes (multiple of 16) from
+ * src to byte offset dst_off_bytes of each of the `world` peer-mapped buffers in the DEVICE array peers */
+int pyglm_peer_push(const void* src, long long nbytes, void* const* peers /*[device]*/, int world, long long dst_off_bytes,
+                    pyglm_stream_t stream);
 int pyglm_gram_tc_stream_tiles(int D, int* tiles /*[host]*/, int capacity);
 int pyglm_gram_tc_quantize(const double* Xp, int ldx, long long T, long long t_off, int D, const double* cmax,
                            unsigned int* xq, unsigned long long* rw, long long Tpad, pyglm_stream_t stream);

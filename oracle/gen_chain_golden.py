@@ -30,7 +30,7 @@ OUT = os.path.join(HERE, "..", "tests", "golden")
 
 CASES = {
     "cfg1": dict(N=4, B=1, L=100, T=10000, sweeps=600, burn=100, seeds=(1, 2, 3, 4, 5, 6), data_seed=0),
-    "cfg2s": dict(N=27, B=3, L=100, T=20000, sweeps=260, burn=60, seeds=(1, 2, 3, 4), data_seed=0),
+    "cfg2s": dict(N=27, B=3, L=100, T=20000, sweeps=450, burn=150, seeds=(1, 2, 3, 4, 5, 6, 7, 8), data_seed=0),
 }
 
 

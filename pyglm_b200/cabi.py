@@ -41,6 +41,8 @@ SIGNATURES = {
     "pyglm_gram_tc_mma": (c_int, [ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_ll, c_int, ptr]),
     "pyglm_gram_tc_mma_probe": (c_int, [ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_ll, ptr]),
     "pyglm_gram_tc_finalize": (c_int, [ptr, c_ll, ptr, ptr, c_int, c_int, c_int, ptr, c_ll, c_int, ptr]),
+    "pyglm_gram_tc_finalize_peers": (c_int, [ptr, c_int, c_ll, c_ll, ptr, ptr, c_int, c_int, c_int, ptr, c_ll, c_int, ptr]),
+    "pyglm_peer_push": (c_int, [ptr, c_ll, ptr, c_int, c_ll, ptr]),
     "pyglm_gram_tc_stream_tiles": (c_int, [c_int, ptr, c_int]),
     "pyglm_gram_tc_quantize": (c_int, [ptr, c_int, c_ll, c_ll, c_int, ptr, ptr, ptr, c_ll, ptr]),
     "pyglm_gram_tc_mma_stream": (c_int, [ptr, ptr, ptr, c_int, c_int, c_ll, c_int, ptr, c_int, ptr, c_ll, c_int, ptr]),

@@ -1088,6 +1088,27 @@ gram_tc_finalize_kernel(const long long* __restrict__ Jint, long long ldjint, co
     J[(long long)n * stride_n + (long long)i * ldj + j] = (double)Jint[(long long)n * ldjint + p] * unit;
 }
 
+// The time-sharded reduce-scatter FUSED into the finalize pass: every rank holds the partial integer sums of ALL neurons
+// over its time slab in a peer-mapped (symmetric) buffer; the owner of a neuron block reads the W partials of its rows
+// straight from the peers' HBM over NVLink (coalesced 8-byte loads along the pair axis), adds them in int64 (exact and
+// order-free: bit-identical to the single-GPU sum) and scales to FP64 in the same pass.  Replaces
+// ncclReduceScatter(int64) + gram_tc_finalize_kernel.  peers[r] = rank r's Jint base; row_off = first row of my block.
+__global__ void __launch_bounds__(256)
+gram_tc_finalize_peers_kernel(const long long* const* __restrict__ peers, int world, long long row_off, long long ldjint,
+                              const double* __restrict__ cmax, const double* __restrict__ omax, int D, int S,
+                              double* __restrict__ J, long long stride_n, int ldj) {
+    const int n = blockIdx.z;
+    const int i = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j > i) return;
+    const long long p = (long long)i * (i + 1) / 2 + j;
+    const long long off = (row_off + n) * ldjint + p;
+    long long tot = 0;
+    for (int r = 0; r < world; ++r) tot += __ldcg(peers[r] + off);
+    const double unit = ldexp((tc_bound(cmax[i]) * tc_bound(cmax[j])) * tc_bound(omax[n]), -8 * S - 8);
+    J[(long long)n * stride_n + (long long)i * ldj + j] = (double)tot * unit;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1461,6 +1482,19 @@ extern "C" int pyglm_gram_tc_finalize(const long long* Jint, long long ldjint, c
     PYGLM_CHECK_ARG(D <= 65535 && n_valid <= 65535 && ldj >= D, "pyglm_gram_tc_finalize: bad geometry");
     dim3 grid((D + 255) / 256, D, n_valid);
     gram_tc_finalize_kernel<<<grid, 256, 0, stream>>>(Jint, ldjint, cmax, omax, D, S, J, stride_n, ldj);
+    PYGLM_LAUNCH_CHECK();
+    return PYGLM_OK;
+}
+
+// J of this rank's neuron block from the partial integer sums of all `world` ranks (peer-mapped buffers): the exact
+// int64 reduce-scatter and the scaling in one kernel.  peers: DEVICE array of `world` Jint base pointers.
+extern "C" int pyglm_gram_tc_finalize_peers(const long long* const* peers, int world, long long row_off, long long ldjint,
+                                            const double* cmax, const double* omax, int D, int n_valid, int S, double* J,
+                                            long long stride_n, int ldj, cudaStream_t stream) {
+    PYGLM_CHECK_ARG(peers && cmax && omax && J && world >= 1 && row_off >= 0, "pyglm_gram_tc_finalize_peers: bad arguments");
+    PYGLM_CHECK_ARG(D <= 65535 && n_valid >= 1 && n_valid <= 65535 && ldj >= D, "pyglm_gram_tc_finalize_peers: bad geometry");
+    dim3 grid((D + 255) / 256, D, n_valid);
+    gram_tc_finalize_peers_kernel<<<grid, 256, 0, stream>>>(peers, world, row_off, ldjint, cmax, omax, D, S, J, stride_n, ldj);
     PYGLM_LAUNCH_CHECK();
     return PYGLM_OK;
 }

@@ -19,7 +19,7 @@ import os
 import numpy as np
 import torch
 
-from .distributed import Comm, block_partition
+from .distributed import Comm, PeerExchange, StateExchange, block_partition
 from .kernels import CudaKernels, gram_tc_bytes, pad_ldn, pad_ldx
 from .priors import prior_arrays
 
@@ -121,6 +121,36 @@ class GibbsEngine(object):
         self._pending = None
         # Optional on-device sample statistics (DeviceMoments); None = off.
         self.moments = None
+        # Exchange steps over peer-mapped memory with our own kernels (distributed.PeerExchange) when the ranks are GPUs
+        # of one NVLink domain; otherwise (gloo CPU tests, PYGLM_PEER_EXCHANGE=0, allocation failure) the NCCL / gloo
+        # collectives of Comm.  All ranks decide alike (the constructor is collective).
+        self.peer = None
+        self._state_xchg = None
+        if PeerExchange.usable(self.comm, self.K.device):
+            ok = 1
+            try:
+                self.peer = PeerExchange(self.comm, self.K)
+                self._state_xchg = StateExchange(self.peer, self.n_max, self._state_width())
+            except Exception as e:                       # pragma: no cover - depends on the box
+                import warnings
+                warnings.warn("peer-memory exchange unavailable (%s): using NCCL collectives" % (e,))
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.K.device)
+            if not bool(self.comm.all_reduce_min(flag).item()):
+                self.peer = self._state_xchg = None
+            else:
+                self.comm.peer = self.peer
+
+    def _state_width(self):
+        """Doubles per state row [a (N) | W (N*B) | b | status], padded to an even count (16-byte rows for the push)."""
+        w = self.N + self.N * self.B + 2
+        return w + (w & 1)
+
+    def _gather_state(self, state):
+        """(n_max, width) rows of this rank's scan block -> (world * n_max, width) rows of all ranks."""
+        if self._state_xchg is not None:
+            return self._state_xchg.all_gather_rows(state)
+        return self.comm.all_gather_rows(state)
 
     def _mark(self, name, start=None):
         if self.profile is None:
@@ -208,7 +238,10 @@ class GibbsEngine(object):
                 plan = self.K.gram_tc_plan(ds.Xp, self.D, n, digits, comm=self.comm, t_off=ds.t_off, stream=stream)
                 # Jint with the row padding the reduce-scatter over the neuron axis needs (extra rows stay zero)
                 rows = self.comm.world * self.n_max
-                if rows != n:
+                if self.peer is not None:
+                    # peer-mapped: the owner of a neuron block reads these partial sums from every rank's HBM
+                    plan.Jint, plan.peer_hdl = self.peer.alloc((rows, plan.geom["Mpad"]), torch.int64, zero=True)
+                elif rows != n:
                     plan.Jint = torch.zeros(rows, plan.geom["Mpad"], dtype=torch.int64, device=self.K.device)
                 return plan
             return self.K.gram_tc_plan(ds.Xp, self.D, n, digits, stream=stream)
@@ -275,7 +308,16 @@ class GibbsEngine(object):
         e1 = self._mark("gram_tc_slice", e0)
         plan.mma()
         e2 = self._mark("gram_tc_mma", e1)
-        if self._time_sharded():
+        if self._time_sharded() and getattr(plan, "peer_hdl", None) is not None:
+            # exact int64 reduce-scatter fused into the finalize pass (csrc/gram_tc.cu gram_tc_finalize_peers_kernel):
+            # barrier (every rank's partial sums are complete) -> read, add, scale -> barrier (the buffers may be reused)
+            nS = self.scan_hi - self.scan_lo
+            self.peer.barrier(plan.peer_hdl, channel=1)
+            if nS > 0:
+                plan.finalize_peers(J, plan.peer_hdl, self.comm.world, self.scan_lo, nS,
+                                    plan.omax[self.scan_lo:self.scan_hi])
+            self.peer.barrier(plan.peer_hdl, channel=1)
+        elif self._time_sharded():
             nS = self.scan_hi - self.scan_lo
             Jloc = self.comm.reduce_scatter_rows(plan.Jint)
             e2 = self._mark("gram_reduce_scatter", e2)
@@ -524,7 +566,7 @@ class GibbsEngine(object):
             if J_S is None and nP > 0:
                 J_S = self._augment(datasets, self.build_Wt(A, W, b, p_lo, p_hi), call_base)
         # new state rows [a (N) | W (N*B) | b | status], one row per neuron of the scan block (padded to n_max)
-        width = N + NB + 2
+        width = self._state_width()
         state = K.zeros(self.n_max if comm.world > 1 else nS, width)
         if nS > 0:
             if datasets:
@@ -561,7 +603,7 @@ class GibbsEngine(object):
             state[:nS, N + NB + 1] = status
         # exchange: ONE all-gather of the new rows (the only collective of the neuron-sharded sweep)
         if comm.world > 1:
-            state = comm.all_gather_rows(state)[:N]
+            state = self._gather_state(state)[:N]
         # state -> host through pinned memory, asynchronously ...
         stage = self._pinned("state", tuple(state.shape), torch.float64)
         stage.copy_(state, non_blocking=True)
@@ -655,7 +697,7 @@ class GibbsEngine(object):
         call_base = self.calls * self.CALL_STRIDE
         self._check_call_ids(datasets)
         self._pending = None
-        width = N + NB + 2
+        width = self._state_width()
         state = K.zeros(self.n_max if comm.world > 1 else nS, width)
         if nS > 0:
             if datasets:
@@ -688,7 +730,7 @@ class GibbsEngine(object):
             state[:nS, N + NB] = b_new
             state[:nS, N + NB + 1] = status
         if comm.world > 1:
-            state = comm.all_gather_rows(state)[:N]
+            state = self._gather_state(state)[:N]
         host = state.cpu().numpy()
         self.d2h_bytes += host.nbytes
         if host[:, N + NB + 1].any():

@@ -359,6 +359,16 @@ class TcGramPlan(object):
                 n, self.S, K._p(J), J.shape[1] * J.shape[2], J.shape[2], K._stream())
         return J
 
+    def finalize_peers(self, J, hdl, world, row_off, n, omax):
+        """J[0:n] = scaled sum over the ranks' peer-mapped Jint rows [row_off, row_off + n): the time-sharded
+        reduce-scatter and the finalize pass as one kernel (hdl: symmetric-memory handle of self.Jint)."""
+        K, g = self.K, self.geom
+        assert J.shape[0] >= n and omax.shape[0] >= n and omax.is_contiguous()
+        K._call("pyglm_gram_tc_finalize_peers", hdl.buffer_ptrs_dev, int(world), int(row_off), g["Mpad"],
+                K._p(self.cmax), K._p(omax), self.D, int(n), self.S, K._p(J), J.shape[1] * J.shape[2], J.shape[2],
+                K._stream())
+        return J
+
     def gram(self, Om, J=None):
         """J[n, i, j] (i >= j) = sum_t Xp[t,i] Xp[t,j] Om[t,n] for Om > 0."""
         if J is None:

@@ -223,6 +223,29 @@ def test_chain_matches_oracle_chain_readme_config():
     np.testing.assert_allclose(g_b, c_b, atol=0.12)
 
 
+@pytest.mark.parametrize("case,seed", [("chains_cfg1.npz", 5), ("chains_cfg1.npz", 6), ("chains_cfg2s.npz", 7),
+                                       ("chains_cfg2s.npz", 8)])
+def test_chain_statistics_match_reference_chains(golden, case, seed):
+    """north_star's chain-level validation: the GPU sampler against long chains of the REFERENCE's own sampler on the
+    same synthetic data (README configuration N=4, and N=27 B=3 T=2e4; fixtures from oracle/gen_chain_golden.py).
+    Two-sample KS on the post-burn-in log-likelihood trace, P(A), E[a W], E[b]; all bounds come from the
+    leave-one-out spread between the reference chains (tests/chain_stats.py), none is hand-set."""
+    from pyglm_b200.models import SparseBernoulliGLM
+    from tests.chain_stats import load_case, summarize, assert_chain_matches_reference
+    g, Y, (T, N, B, L) = load_case(golden, case)
+    sweeps, burn = int(g["sweeps"]), int(g["burn"])
+    np.random.seed(100 + seed)
+    m = SparseBernoulliGLM(N, basis=g["basis"], regression_kwargs=dict(S_w=10.0, mu_b=-2.), seed=seed)
+    m.add_data(Y)
+    rec = ([], [], [], [])
+    for _ in range(sweeps):
+        m.resample_model()
+        for r, v in zip(rec, (m.log_likelihood(), m.adjacency, m.weights, m.biases)):
+            r.append(np.array(v))
+    ll, PA, EW, Eb = summarize(*rec, burn=burn)
+    assert_chain_matches_reference(g, ll, PA, EW, Eb)
+
+
 @pytest.mark.parametrize("N,B,L,T", [(3, 2, 10, 500), (12, 2, 20, 3000), (70, 3, 100, 1500), (400, 2, 30, 300)])
 def test_generate_replays_the_reference_recursion(N, B, L, T):
     """generate() on the device (csrc/generate.cu) against the oracle's restatement of models.py:98-151 driven by

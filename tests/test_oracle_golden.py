@@ -170,3 +170,21 @@ def test_gaussian_regression_matches_reference(golden):
                                                g["eta1"][n]).sum()
     np.testing.assert_allclose(ll0, float(g["ll0"]), rtol=1e-12)
     np.testing.assert_allclose(ll1, float(g["ll1"]), rtol=1e-12)
+
+
+def test_oracle_chain_matches_reference_chains(golden):
+    """The numpy port's own Gibbs chain on the README configuration (BASELINE configs[0]) against six chains of the
+    reference's unmodified sampler on the same data (tests/golden/chains_cfg1.npz): KS on the post-burn-in
+    log-likelihood, P(A), E[a W], E[b], every bound derived from the spread between the reference chains."""
+    from tests.chain_stats import load_case, summarize, assert_chain_matches_reference
+    g, Y, (T, N, B, L) = load_case(golden, "chains_cfg1.npz")
+    sweeps, burn = int(g["sweeps"]), int(g["burn"])
+    m = O.OracleSparseBernoulliGLM(N, g["basis"], S_w=10.0, mu_b=-2.0, seed=21, pg_threads=1)
+    m.add_data(Y)
+    rec = ([], [], [], [])
+    for _ in range(sweeps):
+        m.resample_model()
+        for r, v in zip(rec, (m.log_likelihood(), m.A, m.W, m.bias)):
+            r.append(np.array(v))
+    ll, PA, EW, Eb = summarize(*rec, burn=burn)
+    assert_chain_matches_reference(g, ll, PA, EW, Eb)
