@@ -118,7 +118,7 @@ class ClockSampler(object):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -140,6 +140,8 @@ class ClockSampler(object):
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if not self.samples:
+            time.sleep(0.1)                 # a timed region shorter than nvidia-smi's start-up: take what arrives now
         self.proc.terminate()
         sm = sorted(s[0] for s in self.samples)
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None),
@@ -326,13 +328,13 @@ def main():
     model.resample_model()                               # first sweep: operand build + FP64 cross-check of the Gram
     torch.cuda.synchronize()
     t_first = time.perf_counter()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                  # runs through the warm-up sweeps and both timed regions
     for _ in range(warmup - 1):
         model.resample_model()
     barrier()
     h2d0, d2h0, l0 = eng.h2d_bytes, eng.d2h_bytes, K.launches
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(steps):

@@ -1,0 +1,24 @@
+#!/bin/bash
+# 8-GPU box (gpurun --gpus 8): cfg3 on 8 and 4 ranks (cluster scan kernel + peer-memory exchange), the same with the
+# round-1 configuration of those two pieces for comparison at 8 ranks, and cfg4 on 8 ranks.
+TAG=${1:-r02o}
+mkdir -p gpurun_out
+run() {  # name, nproc, extra env..., -- bench args
+  local name=$1 n=$2; shift 2
+  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700 + RANDOM % 200)) \
+      bench.py --gpus $n --steps 10 --warmup 3 --no-cpu-baseline $BARGS > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/${TAG}_${name}.json").read().strip().splitlines()[-1])
+    print("${name}", "value %.1f e2e %.1f ms %.3f" % (d["value"], d["e2e"]["value"], d["ms_per_step"]), {k: round(v,3) for k,v in d["kernels_ms"].items()})
+except Exception as e:
+    print("${name} FAILED", e); print(open("gpurun_out/${TAG}_${name}.err").read()[-1500:])
+PY
+}
+BARGS=""
+run bench_8gpu 8 A=1
+run bench_8gpu_r1cfg 8 PYGLM_SS_VARIANT=1 PYGLM_PEER_EXCHANGE=0
+run bench_4gpu 4 A=1
+BARGS="--config cfg4 --steps 5"
+run bench_cfg4_8gpu 8 A=1
