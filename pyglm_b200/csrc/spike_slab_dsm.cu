@@ -93,6 +93,7 @@ __device__ __forceinline__ void tile_update(double* Ploc, int ldp, int RL, int n
                                             AF afrag, BF bfrag, CL ctlast) {
     const int g = lane >> 2, q = lane & 3;
     const int ngrp = (nrt >= NWARP) ? 1 : NWARP / nrt;
+    constexpr int U = 4;                                  // column tiles in flight per warp (independent DMMA chains)
     for (int task = warp; task < nrt * ngrp; task += NWARP) {
         const int rt = task / ngrp, cgq = task - rt * ngrp;
         const int lr = rt * 8 + g;
@@ -100,14 +101,29 @@ __device__ __forceinline__ void tile_update(double* Ploc, int ldp, int RL, int n
         const double a1 = (KD == 8) ? afrag(lr, 4 + q) : 0.0;
         const int cend = min(ct1, ctlast(rt) + 1);
         const bool rowok = lr < RL;
-        for (int ct = ct0 + cgq; ct < cend; ct += ngrp) {
-            const int j = ct * 8;
-            const bool ok = rowok && (j + 2 * q + 1 < ldp);
-            double* cp = Ploc + (size_t)lr * ldp + j + 2 * q;
-            double2 c = ok ? *reinterpret_cast<double2*>(cp) : make_double2(0.0, 0.0);
-            dmma884(c.x, c.y, a0, bfrag(q, j + g));
-            if (KD == 8) dmma884(c.x, c.y, a1, bfrag(4 + q, j + g));
-            if (ok) *reinterpret_cast<double2*>(cp) = c;
+        double* rowp = Ploc + (size_t)lr * ldp + 2 * q;
+        for (int ct = ct0 + cgq; ct < cend; ct += U * ngrp) {
+            double2 c[U];
+            double b0[U], b1[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = (ct + u * ngrp) * 8;
+                const bool in = ct + u * ngrp < cend;
+                ok[u] = in && rowok && (j + 2 * q + 1 < ldp);
+                c[u] = ok[u] ? *reinterpret_cast<double2*>(rowp + j) : make_double2(0.0, 0.0);
+                b0[u] = in ? bfrag(q, j + g) : 0.0;
+                b1[u] = (KD == 8 && in) ? bfrag(4 + q, j + g) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) dmma884(c[u].x, c[u].y, a0, b0[u]);
+            if (KD == 8) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) dmma884(c[u].x, c[u].y, a1, b1[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) *reinterpret_cast<double2*>(rowp + (ct + u * ngrp) * 8) = c[u];
         }
     }
 }
@@ -133,8 +149,8 @@ inline DsmGeom dsm_geom(int N, int B, int C) {
         const int FPN = max(GW, LACp) * g.ldp + 8;
         size_t dbl = (size_t)g.RL * g.ldp + FPN + Dp /*mu*/ + 2 * (size_t)XSZ + (size_t)Dp * B /*Pd*/ +
                      2 * (size_t)g.RL * LAC + LAC * LAC + LAC + LAC * B + 3 * B * LAC + B * B + B + (2 * GW * GW + 2 + GW) +
-                     2 * C * GW + 2 * N /*us, cpl*/;
-        size_t bytes = dbl * sizeof(double) + ((size_t)Dp + 3 * N + 8 + 8) * sizeof(int) + (size_t)((N + 7) & ~7);
+                     2 * C * GW + NWARP + 2 * N /*us, cpl*/;
+        size_t bytes = dbl * sizeof(double) + ((size_t)Dp + 3 * N + 8 + 8 + 2 * NWARP) * sizeof(int) + (size_t)((N + 7) & ~7);
         if (bytes <= 227 * 1024) {
             g.LAG = G; g.XSZ = XSZ; g.FPN = FPN; g.smem = bytes;
             break;
@@ -194,6 +210,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
     double* M8 = p; p += 2 * GW * GW + 2;              // two pivot buffers + flag
     double* rd8 = p; p += GW;                          // reciprocals of the pivot's diagonal
     double* spart = p; p += 2 * C * GW;
+    double* blo = p; p += NWARP;                       // log-odds of the batch of speculative evaluations
     double* us_s = p; p += N;
     double* cpl_s = p; p += N;                         // cprior + logit rho
     int* cidx = reinterpret_cast<int*>(p);
@@ -202,7 +219,9 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
     int* perm_s = freel + N;
     int* cand = perm_s + N;
     int* scal = cand + 8;
-    unsigned char* a_s = reinterpret_cast<unsigned char*>(scal + 8);
+    int* bst = scal + 8;                               // per warp: outcome of its speculative evaluation, table slot
+    int* bgs = bst + NWARP;
+    unsigned char* a_s = reinterpret_cast<unsigned char*>(bgs + NWARP);
     // DRAW vectors alias the scan's exchange buffers and diagonal blocks (dead by then; xbuf and Pd are adjacent)
     double* hv = xbuf;
     double* xs = xbuf + Dp;
@@ -355,143 +374,203 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
         // =============================================================== SCAN (regression.py:286-320)
         int par = 0;
         unsigned live = 0u;
-        for (int step = 0; step < N && !fail; ++step) {
-            const int m = perm_s[step];
-            const int pos = slot[m];
-            double S[B][B], r[B], sgn = -1.0;
+        // Evaluations are SPECULATIVELY BATCHED: warp w evaluates scan step `step + w` on the current state, i.e. assuming
+        // that no flip is committed before it (true for most steps: ~40 of 200 flip at cfg3).  The decisions are then
+        // taken in scan order; the first flip is committed and the evaluations behind it are discarded and redone on
+        // the new state.  The serial chain of a step (B x B factorisation, logarithm, comparison) is thus paid once per
+        // flip and once per 16 quiet steps instead of once per step, and it is no longer issued by 16 warps at once.
+        enum { ST_NOFLIP = 0, ST_FLIP = 1, ST_REFILL = 2, ST_FAIL = 3, ST_END = 4 };
+        int step = 0;
+        while (step < N && !fail) {
             SmallSolve<B> w;
-            int g = -1;
-            if (pos >= 0) {
-                // removal: ml(with) - ml(without) read off the replicated diagonal block and mu
+            double r[B];
+            {
+                const int s_w = step + warp;
+                int st = ST_END, g_w = -1;
+                double lo_w = 0.0;
+                if (s_w < N) {
+                    const int m_w = perm_s[s_w];
+                    const int pos_w = slot[m_w];
+                    double S[B][B], sgn = -1.0;
+                    bool have = true;
+                    if (pos_w >= 0) {
+                        // removal: ml(with) - ml(without) read off the replicated diagonal block and mu
 #pragma unroll
-                for (int i = 0; i < B; ++i) {
+                        for (int i = 0; i < B; ++i) {
 #pragma unroll
-                    for (int k = 0; k <= i; ++k) S[i][k] = Pd[(pos + i) * B + k];
-                    r[i] = mu[pos + i];
-                }
-                sgn = 1.0;
-            } else {
+                            for (int k = 0; k <= i; ++k) S[i][k] = Pd[(pos_w + i) * B + k];
+                            r[i] = mu[pos_w + i];
+                        }
+                        sgn = 1.0;
+                    } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g = (i < LAG && ((live >> i) & 1u) && cand[i] == m) ? i : g;
-                if (g < 0) {
-                    // ---- refill the table with the next LAG inactive neurons of the scan (this one first)
-                    DBG_T0;
-                    __syncthreads();
-                    if (tid == 0) {
-                        int q = 0;
-                        for (int i = step; i < N && q < LAG; ++i)
-                            if (slot[perm_s[i]] < 0) cand[q++] = perm_s[i];
-                        scal[1] = q;
-                        for (; q < 8; ++q) cand[q] = -1;
+                        for (int i = 0; i < 8; ++i) g_w = (i < LAG && ((live >> i) & 1u) && cand[i] == m_w) ? i : g_w;
+                        have = g_w >= 0;
+#pragma unroll
+                        for (int b = 0; b < B; ++b) {
+#pragma unroll
+                            for (int b2 = 0; b2 <= b; ++b2)
+                                S[b][b2] = have ? Jgg[(g_w * B + b) * B + b2] - Mt[(g_w * B + b) * LAC + g_w * B + b2] : 1.0;
+                            r[b] = have ? rv[g_w * B + b] : 0.0;
+                        }
                     }
-                    __syncthreads();
-                    live = (1u << scal[1]) - 1u;
-                    const int Ksp = (Ks + 7) & ~7;
-                    for (int e = tid; e < Ksp * LACp; e += NTHR) {   // C[col][i] = Jp[S_i, candidate coordinate], zero padded
+                    if (!have) {
+                        st = ST_REFILL;
+                    } else {
+                        // logodds = sgn 1/2 log|S| + 1/2 r^T S^-1 r + prior terms against the threshold log((1-u)/u) of the
+                        // step; the logarithm in single precision first, in double precision only when the comparison is
+                        // closer than 1e-4 or the log-odds are recorded
+                        double det, qf;
+                        const bool ok = small_factor_parts<B, B>(w, S, r, det, qf);
+                        const double rest = 0.5 * qf + cpl_s[m_w], thr = us_s[s_w];
+                        double lo = sgn * 0.5 * (double)__logf((float)det) + rest;
+                        if (A.logodds != nullptr || !(fabs(lo - thr) > 1e-4) || det < 1e-30 || det > 1e30)
+                            lo = sgn * 0.5 * log(det) + rest;
+                        lo_w = lo;
+                        const int v = lo > thr;
+                        st = (!ok || !(lo == lo)) ? ST_FAIL : (((pos_w < 0) == (v != 0)) ? ST_FLIP : ST_NOFLIP);
+                    }
+                }
+                if (lane == 0) { bst[warp] = st; bgs[warp] = g_w; blo[warp] = lo_w; }
+            }
+            __syncthreads();
+            int first = NWARP;
+#pragma unroll
+            for (int i = NWARP - 1; i >= 0; --i) first = (bst[i] != ST_NOFLIP) ? i : first;
+            const int stf = (first < NWARP) ? bst[first] : ST_NOFLIP;
+            // steps [step, step + first) are evaluated and left as they are; a flip at `first` is decided too
+            const int ndec = first + ((stf == ST_FLIP) ? 1 : 0);
+#pragma unroll
+            for (int i = 0; i < NWARP; ++i)
+                if (i < first && bgs[i] >= 0) live &= ~(1u << bgs[i]);
+            if (A.logodds && crank == 0 && tid < ndec) A.logodds[(size_t)ln * N + step + tid] = blo[tid];
+            if (stf == ST_FAIL) { fail = 1; break; }
+            step += first;
+            if (stf == ST_NOFLIP || stf == ST_END) { __syncthreads(); continue; }
+            if (stf == ST_REFILL) {
+            // ---- refill the table with the next LAG inactive neurons of the scan (this one first)
+            DBG_T0;
+            __syncthreads();
+            if (tid == 0) {
+                int q = 0;
+                for (int i = step; i < N && q < LAG; ++i)
+                    if (slot[perm_s[i]] < 0) cand[q++] = perm_s[i];
+                scal[1] = q;
+                for (; q < 8; ++q) cand[q] = -1;
+            }
+            __syncthreads();
+            live = (1u << scal[1]) - 1u;
+            const int Ksp = (Ks + 7) & ~7;
+            for (int e0 = tid; e0 < Ksp * LACp; e0 += 4 * NTHR) {   // C[col][i] = Jp[S_i, candidate coordinate], 0 padded
+                // four elements per thread with their global loads issued together (one L2 round trip, not four)
+                double v[4];
+                int dst[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * NTHR;
+                    v[u] = 0.0;
+                    dst[u] = -1;
+                    if (e < Ksp * LACp) {
                         const int col = e / Ksp, i = e - col * Ksp;
-                        double v = 0.0;
+                        dst[u] = col * ldp + i;
                         if (col < LAC && i < Ks) {
                             const int gq = col / B, mq = cand[gq], ci = cidx[i];
-                            if (mq >= 0 && ci >= 0) v = Jp(ci, mq * B + (col - gq * B));
-                        }
-                        Fp[col * ldp + i] = v;
-                    }
-                    if (tid < LAC * B) {
-                        const int col = tid / B, b2 = tid - col * B, gq = col / B, mq = cand[gq];
-                        Jgg[tid] = (mq >= 0) ? Jp(mq * B + (col - gq * B), mq * B + b2) : 1.0;
-                    }
-                    __syncthreads();
-                    if (dbgon) dbg[11] += clock64() - t0__;
-                    {
-                        // my rows of T = P C on the tensor cores: one warp per (row tile, 8 table columns), two independent
-                        // accumulator pairs over the even / odd k-steps
-                        const int nrt = ((Ks - crank + C - 1) / C + 7) / 8, nctl = LACp / 8;
-                        const int gq = lane >> 2, q = lane & 3;
-                        for (int task = warp; task < nrt * nctl; task += NWARP) {
-                            const int rt = task / nctl, ctl = task - rt * nctl;
-                            const int lr = rt * 8 + gq, i = lr * C + crank;
-                            const bool rowok = i < Ks;
-                            const double* prow = Ploc + (size_t)(rowok ? lr : 0) * ldp;
-                            const double* crow = Fp + (size_t)(ctl * 8 + gq) * ldp;
-                            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-                            for (int j0 = 0; j0 < Ks; j0 += 8) {
-                                const double a0 = (rowok && j0 + q < Ks) ? prow[j0 + q] : 0.0;
-                                const double a1 = (rowok && j0 + 4 + q < Ks) ? prow[j0 + 4 + q] : 0.0;
-                                dmma884(c0, c1, a0, crow[j0 + q]);
-                                dmma884(d0, d1, a1, crow[j0 + 4 + q]);
-                            }
-                            c0 += d0; c1 += d1;
-                            const int col = ctl * 8 + 2 * q;
-                            if (rowok) {
-                                if (col < LAC) Tloc[lr * LAC + col] = c0;
-                                if (col + 1 < LAC) Tloc[lr * LAC + col + 1] = c1;
+                            if (mq >= 0 && ci >= 0) {
+                                const int cj = mq * B + (col - gq * B);      // candidate coordinates are inactive: ci != cj
+                                const int hi = max(ci, cj), lo = min(ci, cj);
+                                v[u] = Jn[(size_t)hi * ldj + lo];            // off-block entries carry no prior term
                             }
                         }
-                        for (int e = tid; e < RL * LAC; e += NTHR) {
-                            const int lr = e / LAC, c2 = e - lr * LAC, i = lr * C + crank;
-                            if (i < Ks) Cloc[e] = Fp[c2 * ldp + i];
-                        }
                     }
-                    __syncthreads();
-                    if (dbgon) dbg[12] += clock64() - t0__;
-                    // partial sums over my rows of M = T^T C and C^T mu -> every CTA; then summed in rank order
-                    double* xb = xbuf + (size_t)par * XSZ;
-                    if (tid < LAC * LAC + LAC) {
-                        double s0 = 0.0, s1 = 0.0;
-                        if (tid < LAC * LAC) {
-                            const int c1 = tid / LAC, c2 = tid - c1 * LAC;
-                            int lr = 0;
-                            for (; (lr + 1) * C + crank < Ks; lr += 2) {
-                                s0 += Tloc[lr * LAC + c1] * Cloc[lr * LAC + c2];
-                                s1 += Tloc[(lr + 1) * LAC + c1] * Cloc[(lr + 1) * LAC + c2];
-                            }
-                            if (lr * C + crank < Ks) s0 += Tloc[lr * LAC + c1] * Cloc[lr * LAC + c2];
-                        } else {
-                            const int c2 = tid - LAC * LAC;
-                            for (int lr = 0; lr * C + crank < Ks; ++lr) s0 += Cloc[lr * LAC + c2] * mu[lr * C + crank];
-                        }
-                        store_all<C>(cl, &xb[crank * (LAC * LAC + LAC) + tid], s0 + s1);
-                    }
-                    if (dbgon) dbg[13] += clock64() - t0__;
-                    cl.sync();
-                    if (dbgon) dbg[14] += clock64() - t0__;
-                    if (tid < LAC * LAC + LAC) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int rr = 0; rr < C; ++rr) s += xb[rr * (LAC * LAC + LAC) + tid];
-                        if (tid < LAC * LAC) {
-                            Mt[tid] = s;
-                        } else {
-                            const int c2 = tid - LAC * LAC, gq = c2 / B, mq = cand[gq];
-                            rv[c2] = (mq >= 0) ? hp(mq * B + (c2 - gq * B)) - s : 0.0;
-                        }
-                    }
-                    __syncthreads();
-                    par ^= 1;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) g = (i < LAG && ((live >> i) & 1u) && cand[i] == m) ? i : g;
-                    DBG_ACC(4);
-                    if (dbgon) ++dbg[8];
                 }
 #pragma unroll
-                for (int b = 0; b < B; ++b) {
-#pragma unroll
-                    for (int b2 = 0; b2 <= b; ++b2) S[b][b2] = Jgg[(g * B + b) * B + b2] - Mt[(g * B + b) * LAC + g * B + b2];
-                    r[b] = rv[g * B + b];
+                for (int u = 0; u < 4; ++u)
+                    if (dst[u] >= 0) Fp[dst[u]] = v[u];
+            }
+            if (tid < LAC * B) {
+                const int col = tid / B, b2 = tid - col * B, gq = col / B, mq = cand[gq];
+                Jgg[tid] = (mq >= 0) ? Jp(mq * B + (col - gq * B), mq * B + b2) : 1.0;
+            }
+            __syncthreads();
+            if (dbgon) dbg[11] += clock64() - t0__;
+            {
+                // my rows of T = P C on the tensor cores: one warp per (row tile, 8 table columns), two independent
+                // accumulator pairs over the even / odd k-steps
+                const int nrt = ((Ks - crank + C - 1) / C + 7) / 8, nctl = LACp / 8;
+                const int gq = lane >> 2, q = lane & 3;
+                for (int task = warp; task < nrt * nctl; task += NWARP) {
+                    const int rt = task / nctl, ctl = task - rt * nctl;
+                    const int lr = rt * 8 + gq, i = lr * C + crank;
+                    const bool rowok = i < Ks;
+                    const double* prow = Ploc + (size_t)(rowok ? lr : 0) * ldp;
+                    const double* crow = Fp + (size_t)(ctl * 8 + gq) * ldp;
+                    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+                    for (int j0 = 0; j0 < Ks; j0 += 8) {
+                        const double a0 = (rowok && j0 + q < Ks) ? prow[j0 + q] : 0.0;
+                        const double a1 = (rowok && j0 + 4 + q < Ks) ? prow[j0 + 4 + q] : 0.0;
+                        dmma884(c0, c1, a0, crow[j0 + q]);
+                        dmma884(d0, d1, a1, crow[j0 + 4 + q]);
+                    }
+                    c0 += d0; c1 += d1;
+                    const int col = ctl * 8 + 2 * q;
+                    if (rowok) {
+                        if (col < LAC) Tloc[lr * LAC + col] = c0;
+                        if (col + 1 < LAC) Tloc[lr * LAC + col + 1] = c1;
+                    }
+                }
+                for (int e = tid; e < RL * LAC; e += NTHR) {
+                    const int lr = e / LAC, c2 = e - lr * LAC, i = lr * C + crank;
+                    if (i < Ks) Cloc[e] = Fp[c2 * ldp + i];
                 }
             }
-            // logodds = sgn 1/2 log|S| + 1/2 r^T S^-1 r + prior terms against the threshold of this step.  The logarithm is
-            // taken in single precision first (every thread of every CTA runs this chain: it is the serial part of a step)
-            // and in double precision only when the comparison is closer than 1e-4 or the log-odds are recorded.
-            double det, qf;
-            if (!small_factor_parts<B, B>(w, S, r, det, qf)) { fail = 1; break; }
-            const double rest = 0.5 * qf + cpl_s[m], thr = us_s[step];
-            double lo = sgn * 0.5 * (double)__logf((float)det) + rest;
-            if (A.logodds != nullptr || !(fabs(lo - thr) > 1e-4) || det < 1e-30 || det > 1e30)
-                lo = sgn * 0.5 * log(det) + rest;
-            if (!(lo == lo)) { fail = 1; break; }
-            const int v = lo > thr;
-            if (A.logodds && tid == 0 && crank == 0) A.logodds[(size_t)ln * N + step] = lo;
+            __syncthreads();
+            if (dbgon) dbg[12] += clock64() - t0__;
+            // partial sums over my rows of M = T^T C and C^T mu -> every CTA; then summed in rank order
+            double* xb = xbuf + (size_t)par * XSZ;
+            if (tid < LAC * LAC + LAC) {
+                double s0 = 0.0, s1 = 0.0;
+                if (tid < LAC * LAC) {
+                    const int c1 = tid / LAC, c2 = tid - c1 * LAC;
+                    int lr = 0;
+                    for (; (lr + 1) * C + crank < Ks; lr += 2) {
+                        s0 += Tloc[lr * LAC + c1] * Cloc[lr * LAC + c2];
+                        s1 += Tloc[(lr + 1) * LAC + c1] * Cloc[(lr + 1) * LAC + c2];
+                    }
+                    if (lr * C + crank < Ks) s0 += Tloc[lr * LAC + c1] * Cloc[lr * LAC + c2];
+                } else {
+                    const int c2 = tid - LAC * LAC;
+                    for (int lr = 0; lr * C + crank < Ks; ++lr) s0 += Cloc[lr * LAC + c2] * mu[lr * C + crank];
+                }
+                store_all<C>(cl, &xb[crank * (LAC * LAC + LAC) + tid], s0 + s1);
+            }
+            if (dbgon) dbg[13] += clock64() - t0__;
+            cl.sync();
+            if (dbgon) dbg[14] += clock64() - t0__;
+            if (tid < LAC * LAC + LAC) {
+                double s = 0.0;
+#pragma unroll
+                for (int rr = 0; rr < C; ++rr) s += xb[rr * (LAC * LAC + LAC) + tid];
+                if (tid < LAC * LAC) {
+                    Mt[tid] = s;
+                } else {
+                    const int c2 = tid - LAC * LAC, gq = c2 / B, mq = cand[gq];
+                    rv[c2] = (mq >= 0) ? hp(mq * B + (c2 - gq * B)) - s : 0.0;
+                }
+            }
+            __syncthreads();
+            par ^= 1;
+            DBG_ACC(4);
+                if (dbgon) ++dbg[8];
+                __syncthreads();
+                continue;
+            }
+            // ---- a flip of scan step `step`, evaluated by warp `first` (whose registers hold the factorisation)
+            const int m = perm_s[step];
+            const int pos = slot[m];
+            const int g = bgs[first];
+            const bool fw = (warp == first);
+            const int v = (pos < 0) ? 1 : 0;
+            ++step;
 
             if (pos < 0 && v) {
                 // ---- commit the addition of slot g (block m)
@@ -512,7 +591,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                     Dsh[tid] = d;
                     Esh[tid] = lv ? Mt[(g * B + b) * LAC + c2] - d : 0.0;
                 }
-                if (tid == 0) {
+                if (fw && lane == 0) {
 #pragma unroll
                     for (int i = 0; i < B; ++i) {
                         grsh[i] = w.gr[i];
@@ -660,7 +739,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                         if (tid < LAC) store_all<C>(cl, &vs[b * LAC + tid], Tloc[lr * LAC + tid]);
                     }
                 }
-                if (tid == 0) {
+                if (fw && lane == 0) {
 #pragma unroll
                     for (int i = 0; i < B; ++i) {
                         grsh[i] = w.gr[i];
@@ -771,8 +850,6 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                 __syncthreads();
                 DBG_ACC(6);
                 if (dbgon) ++dbg[10];
-            } else if (pos < 0) {
-                live &= ~(1u << g);                                      // evaluated and left inactive
             }
         }
         if (A.debug) clk2 = clock64();
