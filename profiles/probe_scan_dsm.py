@@ -71,7 +71,7 @@ res = []
 for n_loc in [int(x) for x in os.environ.get("PROBE_NLOC", "200,100,50,25").split(",")]:
     t_old, o_old = run("1", n_loc)
     row = dict(n_loc=n_loc, one_cta_ms=t_old)
-    for v in ("88",):
+    for v in os.environ.get("PROBE_VARIANTS", "84,88").split(","):
         t_new, o_new = run(v, n_loc)
         row["cluster%s_ms" % v[1]] = t_new
         row["adjacency_equal"] = bool(np.array_equal(o_old[0], o_new[0]))

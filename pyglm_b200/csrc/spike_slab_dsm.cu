@@ -88,8 +88,8 @@ __device__ __forceinline__ bool chol8(double* M8, int lane, int w) {
 // tiles [ct0, ct1) of 8, row tile rt stopping after column tile ctlast(rt).  A warp keeps its A fragment and walks a
 // strided subset of the column tiles.  a(lr, k) must return 0 for rows that are not to be touched; columns beyond the
 // matrix receive garbage that nobody reads.
-template <int KD, class AF, class BF, class CL>
-__device__ __forceinline__ void tile_update(double* Ploc, int ldp, int RL, int nrt, int ct0, int ct1, int warp, int lane,
+template <int KD, class RP, class RN, class AF, class BF, class CL>
+__device__ __forceinline__ void tile_update(RP rowptr, RN rowlen, int RL, int nrt, int ct0, int ct1, int warp, int lane,
                                             AF afrag, BF bfrag, CL ctlast) {
     const int g = lane >> 2, q = lane & 3;
     const int ngrp = (nrt >= NWARP) ? 1 : NWARP / nrt;
@@ -101,7 +101,8 @@ __device__ __forceinline__ void tile_update(double* Ploc, int ldp, int RL, int n
         const double a1 = (KD == 8) ? afrag(lr, 4 + q) : 0.0;
         const int cend = min(ct1, ctlast(rt) + 1);
         const bool rowok = lr < RL;
-        double* rowp = Ploc + (size_t)lr * ldp + 2 * q;
+        double* rowp = rowptr(rowok ? lr : 0) + 2 * q;
+        const int rlen = rowlen(rowok ? lr : 0);           // allocated entries of the row (full rows: the pitch)
         for (int ct = ct0 + cgq; ct < cend; ct += U * ngrp) {
             double2 c[U];
             double b0[U], b1[U];
@@ -110,7 +111,7 @@ __device__ __forceinline__ void tile_update(double* Ploc, int ldp, int RL, int n
             for (int u = 0; u < U; ++u) {
                 const int j = (ct + u * ngrp) * 8;
                 const bool in = ct + u * ngrp < cend;
-                ok[u] = in && rowok && (j + 2 * q + 1 < ldp);
+                ok[u] = in && rowok && (j + 2 * q + 1 < rlen);
                 c[u] = ok[u] ? *reinterpret_cast<double2*>(rowp + j) : make_double2(0.0, 0.0);
                 b0[u] = in ? bfrag(q, j + g) : 0.0;
                 b1[u] = (KD == 8 && in) ? bfrag(4 + q, j + g) : 0.0;
@@ -129,12 +130,12 @@ __device__ __forceinline__ void tile_update(double* Ploc, int ldp, int RL, int n
 }
 
 struct DsmGeom {
-    int RL, ldp, LAG, XSZ, FPN;     // local rows, row pitch of Ploc, table slots, doubles per exchange buffer, doubles of Fp
+    int RL, ldp, LAG, XSZ, FPN, PSZ, TG;   // TG: thresholds / prior terms of the scan steps in global scratch, not smem     // local rows, row pitch of Ploc, table slots, doubles per exchange buffer, doubles of Fp
     size_t smem;
 };
 
 // Shared-memory plan for (N, B, C); LAG = 0 when even one table slot does not fit.
-inline DsmGeom dsm_geom(int N, int B, int C) {
+inline DsmGeom dsm_geom(int N, int B, int C, bool sym) {
     DsmGeom g;
     const int D = N * B + 1, Dp = (D + 1) & ~1;
     g.RL = (D + C - 1) / C;
@@ -146,22 +147,39 @@ inline DsmGeom dsm_geom(int N, int B, int C) {
         const int LAC = G * B, LACp = (LAC + 7) & ~7;
         int XSZ = max(B * g.ldp + B * LAC, C * (LAC * LAC + LAC));
         XSZ = max(XSZ, (4 * Dp - Dp * B + 1) / 2);      // the DRAW's four K-vectors alias xbuf + Pd
-        const int FPN = max(GW, LACp) * g.ldp + 8;
-        size_t dbl = (size_t)g.RL * g.ldp + FPN + Dp /*mu*/ + 2 * (size_t)XSZ + (size_t)Dp * B /*Pd*/ +
-                     2 * (size_t)g.RL * LAC + LAC * LAC + LAC + LAC * B + 3 * B * LAC + B * B + B + (2 * GW * GW + 2 + GW) +
-                     2 * C * GW + NWARP + 2 * N /*us, cpl*/;
-        size_t bytes = dbl * sizeof(double) + ((size_t)Dp + 3 * N + 8 + 8 + 2 * NWARP) * sizeof(int) + (size_t)((N + 7) & ~7);
-        if (bytes <= 227 * 1024) {
-            g.LAG = G; g.XSZ = XSZ; g.FPN = FPN; g.smem = bytes;
-            break;
+        int FPN = max(GW, LACp) * g.ldp + 8;
+        if (sym) FPN = max(FPN, max(C * Dp, C * g.RL * LAC));   // mu partials / transposed-part exchange of the refill
+        // P: full rows of pitch ldp, or (sym) the lower triangle: row lr of CTA c holds lr C + ((c + 2) & ~1) entries
+        size_t psz = (size_t)g.RL * g.ldp;
+        if (sym) {
+            psz = 0;
+            for (int c = 0; c < C; ++c) {
+                const size_t nr = (D - c + C - 1) / C, l0 = (c + 2) & ~1;        // rows of CTA c, its first row's length
+                psz = max(psz, (size_t)(C / 2) * nr * (nr - 1) + nr * l0);
+            }
         }
+        if (sym && ((D + 7) / 8) * (LACp / 8) > 8 * NWARP) continue;     // register-held partial tiles of the SYM refill
+        bool found = false;
+        for (int tg = 0; tg < 2 && !found; ++tg) {
+            // tg = 1: the per-step thresholds and prior terms (2 N doubles) stay in global scratch (the unused P
+            // workspace): one more table slot is worth more than their shared-memory latency
+            size_t dbl = psz + FPN + Dp /*mu*/ + 2 * (size_t)XSZ + (size_t)Dp * B /*Pd*/ +
+                         2 * (size_t)g.RL * LAC + LAC * LAC + LAC + LAC * B + 3 * B * LAC + B * B + B + (2 * GW * GW + 2 + GW) +
+                         2 * C * GW + NWARP + (tg ? 0 : 2 * N) /*thr, cpl*/;
+            size_t bytes = dbl * sizeof(double) + ((size_t)Dp + 3 * N + 8 + 8 + 2 * NWARP) * sizeof(int) + (size_t)((N + 7) & ~7);
+            if (bytes <= 227 * 1024) {
+                g.LAG = G; g.XSZ = XSZ; g.FPN = FPN; g.PSZ = (int)psz; g.TG = tg; g.smem = bytes;
+                found = true;
+            }
+        }
+        if (found) break;
     }
     return g;
 }
 
-template <int B, int C>
+template <int B, int C, bool SYM>
 __global__ void __launch_bounds__(NTHR, 1)
-spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FPN) {
+spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FPN, int PSZ, int TG) {
     extern __shared__ __align__(16) double sm[];
     cg::cluster_group cl = cg::this_cluster();
     const int crank = (int)cl.block_rank();
@@ -192,7 +210,13 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
 
     // ---- shared memory
     double* p = sm;
-    double* Ploc = p; p += (size_t)RL * ldp;          // my rows of P (slot space), full rows
+    double* Ploc = p; p += PSZ;                        // my rows of P (slot space): full rows, or (SYM) their lower triangle
+    // SYM: row lr (global row i = lr C + crank) keeps its entries j <= i, padded to an even count; row offsets in closed form
+    const int L0 = (crank + 2) & ~1;
+    auto PR = [&](int lr) -> double* {
+        return Ploc + (SYM ? (size_t)(C / 2) * lr * (lr - 1) + (size_t)lr * L0 : (size_t)lr * ldp);
+    };
+    auto PLEN = [&](int lr) -> int { return SYM ? lr * C + L0 : ldp; };
     double* Fp = p; p += FPN;                          // BUILD / DRAW: column panel F[b][j]; SCAN refill: C[col][j] (transient)
     double* mu = p; p += Dp;                           // replicated
     double* xbuf = p; p += 2 * (size_t)XSZ;            // two exchange buffers written by every CTA of the cluster
@@ -211,8 +235,11 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
     double* rd8 = p; p += GW;                          // reciprocals of the pivot's diagonal
     double* spart = p; p += 2 * C * GW;
     double* blo = p; p += NWARP;                       // log-odds of the batch of speculative evaluations
-    double* us_s = p; p += N;
-    double* cpl_s = p; p += N;                         // cprior + logit rho
+    // thresholds log((1 - u) / u) of the scan steps and cprior + logit rho per neuron: shared memory, or (TG) this
+    // neuron's slice of the global P workspace, which the cluster kernel does not otherwise use
+    double* us_s = TG ? A.P + (size_t)ln * D * D : p;
+    double* cpl_s = us_s + N;
+    if (!TG) p += 2 * N;
     int* cidx = reinterpret_cast<int*>(p);
     int* slot = cidx + Dp;
     int* freel = slot + N;
@@ -240,9 +267,9 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
             // a_m = 1  <=>  u > 1 / (1 + exp(logodds))  <=>  logodds > log((1 - u) / u): the per-step exp becomes a
             // threshold computed once, in parallel (sample_discrete_from_log with the uniform u, regression.py:315)
             const double u = A.us[(size_t)ln * N + m];
-            us_s[m] = (u > 0.0) ? log((1.0 - u) / u) : 1e300;
+            if (!TG || crank == 0) us_s[m] = (u > 0.0) ? log((1.0 - u) / u) : 1e300;
         }
-        cpl_s[m] = A.cprior[(size_t)ln * N + m] + A.logit_rho[(size_t)ln * N + m];
+        if (!TG || crank == 0) cpl_s[m] = A.cprior[(size_t)ln * N + m] + A.logit_rho[(size_t)ln * N + m];
     }
     if (tid < 8) cand[tid] = -1;
     __syncthreads();
@@ -276,25 +303,49 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
             const int K = Ks;
             const int nrt = ((K - crank + C - 1) / C + 7) / 8;     // row tiles that hold rows of mine
             for (int lr = warp; lr * C + crank < K; lr += NWARP) {
-                const int ci = cidx[lr * C + crank];
-                double* row = Ploc + (size_t)lr * ldp;
-                for (int j = lane; j < K; j += 32) row[j] = Jp(ci, cidx[j]);
+                const int i = lr * C + crank, ci = cidx[i];
+                double* row = PR(lr);
+                const int jend = SYM ? i + 1 : K;
+                for (int j = lane; j < jend; j += 32) row[j] = Jp(ci, cidx[j]);
             }
             for (int j = tid; j < K; j += NTHR) hv[j] = hp(cidx[j]);
             __syncthreads();
+            auto row_limit = [&](int rt) -> int { return SYM ? ((rt * 8 + 7) * C + crank) / 8 : (1 << 30); };
             for (int k0 = 0; k0 < K; k0 += GW) {
                 const int w = min(GW, K - k0), k1 = k0 + w;
                 long long tb0 = dbgon ? clock64() : 0;
-                for (int e = tid; e < RL * GW; e += NTHR) {      // all-gather the column panel F[b][j] = A[j][k0 + b]
-                    const int lr = e / GW, b = e - lr * GW, j = lr * C + crank;
-                    if (j < K) store_all<C>(cl, &Fp[b * ldp + j], b < w ? Ploc[(size_t)lr * ldp + k0 + b] : 0.0);
+                // all-gather the column panel F[b][j] = A[j][k0 + b] (= A[k0 + b][j]: A is symmetric)
+                if (!SYM) {
+                    for (int e = tid; e < RL * GW; e += NTHR) {
+                        const int lr = e / GW, b = e - lr * GW, j = lr * C + crank;
+                        if (j < K) store_all<C>(cl, &Fp[b * ldp + j], b < w ? PR(lr)[k0 + b] : 0.0);
+                    }
+                } else {
+                    // rows j >= k1 hold A[j][k0 + b] themselves; for j < k0 it sits in pivot row k0 + b, whose owner sends
+                    // the row's left part; the pivot block's lower triangle goes to the second pivot buffer
+                    for (int e = tid; e < RL * GW; e += NTHR) {
+                        const int lr = e / GW, b = e - lr * GW, j = lr * C + crank;
+                        if (j < K && j >= k0) store_all<C>(cl, &Fp[b * ldp + j], (j >= k1 && b < w) ? PR(lr)[k0 + b] : 0.0);
+                    }
+#pragma unroll
+                    for (int b = 0; b < GW; ++b) {
+                        if (b < w && (k0 + b) % C == crank) {
+                            const double* row = PR((k0 + b) / C);
+                            for (int j = tid; j < k0; j += NTHR) store_all<C>(cl, &Fp[b * ldp + j], row[j]);
+                            if (tid <= b) store_all<C>(cl, &M8[GW * GW + b * GW + tid], row[k0 + tid]);
+                        } else if (b >= w) {
+                            if (crank == 0) for (int j = tid; j < k0; j += NTHR) store_all<C>(cl, &Fp[b * ldp + j], 0.0);
+                        }
+                    }
                 }
                 if (dbgon) { const long long t = clock64(); dbg[0] += t - tb0; tb0 = t; }
                 cl.sync();
                 if (dbgon) { const long long t = clock64(); dbg[1] += t - tb0; tb0 = t; }
                 if (tid < GW * GW) {
                     const int r = tid / GW, c = tid - r * GW;
-                    M8[tid] = (r < w && c < w) ? Fp[c * ldp + k0 + r] : (r == c ? 1.0 : 0.0);
+                    double v = (r == c) ? 1.0 : 0.0;
+                    if (r < w && c < w) v = SYM ? M8[GW * GW + max(r, c) * GW + min(r, c)] : Fp[c * ldp + k0 + r];
+                    M8[tid] = v;
                 }
                 __syncthreads();
                 if (warp == 0) {
@@ -306,7 +357,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                 if (dbgon) { const long long t = clock64(); dbg[2] += t - tb0; tb0 = t; }
                 // sweep step on my rows: T = A_op D;  A_oo -= T A_po;  A_op = T, A_po = T^T;  A_pp = -D.
                 // A_oo -= T F on the tensor cores (everything, pivot rows and columns included: they are rewritten below)
-                tile_update<8>(Ploc, ldp, RL, nrt, 0, (K + 7) / 8, warp, lane,
+                tile_update<8>(PR, PLEN, RL, nrt, 0, (K + 7) / 8, warp, lane,
                     [&](int lr, int k) -> double {
                         const int i = lr * C + crank;
                         if (i >= K || (i >= k0 && i < k1)) return 0.0;
@@ -315,23 +366,24 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                         for (int c = 0; c < GW; ++c) v -= Fp[c * ldp + i] * M8[c * GW + k];
                         return v;
                     },
-                    [&](int k, int j) -> double { return Fp[k * ldp + j]; }, no_limit);
+                    [&](int k, int j) -> double { return Fp[k * ldp + j]; }, row_limit);
                 __syncthreads();
                 for (int e = tid; e < RL * GW; e += NTHR) {      // pivot columns of my other rows: A_op = T
                     const int lr = e / GW, b = e - lr * GW, i = lr * C + crank;
-                    if (i < K && !(i >= k0 && i < k1) && b < w) {
+                    if (i < K && !(i >= k0 && i < k1) && b < w && (!SYM || i >= k1)) {
                         double v = 0.0;
 #pragma unroll
                         for (int c = 0; c < GW; ++c) v += Fp[c * ldp + i] * M8[c * GW + b];
-                        Ploc[(size_t)lr * ldp + k0 + b] = v;
+                        PR(lr)[k0 + b] = v;
                     }
                 }
 #pragma unroll
                 for (int r = 0; r < GW; ++r) {                    // pivot rows of mine: A_po = T^T, A_pp = -D
                     const int i = k0 + r;
                     if (r < w && i % C == crank) {
-                        double* row = Ploc + (size_t)(i / C) * ldp;
-                        for (int j = tid; j < K; j += NTHR) {
+                        double* row = PR(i / C);
+                        const int jend = SYM ? i + 1 : K;
+                        for (int j = tid; j < jend; j += NTHR) {
                             double v;
                             if (j >= k0 && j < k1) {
                                 v = -M8[r * GW + (j - k0)];
@@ -350,23 +402,62 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
             }
             if (!fail) {
                 // the sweeps leave -(Jp_SS)^-1: negate, mu = P hp_S, and the replicated diagonal blocks
-                for (int lr = warp; lr * C + crank < K; lr += NWARP) {
-                    const int i = lr * C + crank;
-                    double* row = Ploc + (size_t)lr * ldp;
-                    double acc = 0.0;
-                    for (int j = lane; j < K; j += 32) {
-                        const double v = -row[j];
-                        row[j] = v;
-                        acc += v * hv[j];
+                if (!SYM) {
+                    for (int lr = warp; lr * C + crank < K; lr += NWARP) {
+                        const int i = lr * C + crank;
+                        double* row = PR(lr);
+                        double acc = 0.0;
+                        for (int j = lane; j < K; j += 32) {
+                            const double v = -row[j];
+                            row[j] = v;
+                            acc += v * hv[j];
+                        }
+                        acc = warp_sum(acc);
+                        __syncwarp();
+                        if (lane == 0) store_all<C>(cl, &mu[i], acc);
+                        const int bs = (i == 0) ? 0 : i - ((i - 1) % B);
+                        const int nb = (i == 0) ? 1 : B;
+                        if (lane < nb) store_all<C>(cl, &Pd[i * B + lane], row[bs + lane]);
                     }
-                    acc = warp_sum(acc);
-                    __syncwarp();
-                    if (lane == 0) store_all<C>(cl, &mu[i], acc);
-                    const int bs = (i == 0) ? 0 : i - ((i - 1) % B);
-                    const int nb = (i == 0) ? 1 : B;
-                    if (lane < nb) store_all<C>(cl, &Pd[i * B + lane], row[bs + lane]);
+                    cl.sync();
+                } else {
+                    // lower triangle only: mu_j = sum_{i >= j} P_ij h_i (down my part of column j) + sum_{j' < j} P_jj' h_j'
+                    // (along row j if it is mine); the CTAs' partial vectors are summed in rank order by everyone
+                    double* pm = xbuf + Dp;                              // K partial sums (xs's place: free until the DRAW)
+                    for (int lr = warp; lr * C + crank < K; lr += NWARP) {
+                        const int i = lr * C + crank;
+                        double* row = PR(lr);
+                        for (int j = lane; j <= i; j += 32) row[j] = -row[j];
+                    }
+                    __syncthreads();
+                    for (int j = tid; j < K; j += NTHR) {
+                        double acc = 0.0;
+                        for (int lr = (j - crank + C - 1 >= 0) ? max(0, (j - crank + C - 1) / C) : 0; lr * C + crank < K; ++lr)
+                            acc += PR(lr)[j] * hv[lr * C + crank];
+                        pm[j] = acc;
+                    }
+                    __syncthreads();
+                    for (int lr = warp; lr * C + crank < K; lr += NWARP) {
+                        const int i = lr * C + crank;
+                        const double* row = PR(lr);
+                        double acc = 0.0;
+                        for (int j = lane; j < i; j += 32) acc += row[j] * hv[j];
+                        acc = warp_sum(acc);
+                        if (lane == 0) pm[i] += acc;
+                        const int bs = (i == 0) ? 0 : i - ((i - 1) % B);
+                        if (lane <= i - bs) store_all<C>(cl, &Pd[i * B + lane], row[bs + lane]);
+                    }
+                    __syncthreads();
+                    for (int j = tid; j < K; j += NTHR) store_all<C>(cl, &Fp[crank * Dp + j], pm[j]);
+                    cl.sync();
+                    for (int j = tid; j < K; j += NTHR) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int rr = 0; rr < C; ++rr) acc += Fp[rr * Dp + j];
+                        mu[j] = acc;
+                    }
+                    cl.sync();                                          // Fp is read by everyone before it is reused
                 }
-                cl.sync();
             }
         }
         if (A.debug) clk1 = clock64();
@@ -391,6 +482,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                 if (s_w < N) {
                     const int m_w = perm_s[s_w];
                     const int pos_w = slot[m_w];
+                    const double cplv = cpl_s[m_w], thr = us_s[s_w];        // issued first: they may live in global memory
                     double S[B][B], sgn = -1.0;
                     bool have = true;
                     if (pos_w >= 0) {
@@ -422,7 +514,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                         // closer than 1e-4 or the log-odds are recorded
                         double det, qf;
                         const bool ok = small_factor_parts<B, B>(w, S, r, det, qf);
-                        const double rest = 0.5 * qf + cpl_s[m_w], thr = us_s[s_w];
+                        const double rest = 0.5 * qf + cplv;
                         double lo = sgn * 0.5 * (double)__logf((float)det) + rest;
                         if (A.logodds != nullptr || !(fabs(lo - thr) > 1e-4) || det < 1e-30 || det > 1e30)
                             lo = sgn * 0.5 * log(det) + rest;
@@ -502,12 +594,15 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                     const int rt = task / nctl, ctl = task - rt * nctl;
                     const int lr = rt * 8 + gq, i = lr * C + crank;
                     const bool rowok = i < Ks;
-                    const double* prow = Ploc + (size_t)(rowok ? lr : 0) * ldp;
+                    const double* prow = PR(rowok ? lr : 0);
                     const double* crow = Fp + (size_t)(ctl * 8 + gq) * ldp;
                     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-                    for (int j0 = 0; j0 < Ks; j0 += 8) {
-                        const double a0 = (rowok && j0 + q < Ks) ? prow[j0 + q] : 0.0;
-                        const double a1 = (rowok && j0 + 4 + q < Ks) ? prow[j0 + 4 + q] : 0.0;
+                    const int jlim = SYM ? min(Ks, i + 1) : Ks;          // SYM: the stored part of the row (j <= i)
+                    // the trip count must be the same for all lanes (mma.sync): run to the longest row of the tile
+                    const int jmax = SYM ? min(Ks, (rt * 8 + 7) * C + crank + 1) : Ks;
+                    for (int j0 = 0; j0 < jmax; j0 += 8) {
+                        const double a0 = (rowok && j0 + q < jlim) ? prow[j0 + q] : 0.0;
+                        const double a1 = (rowok && j0 + 4 + q < jlim) ? prow[j0 + 4 + q] : 0.0;
                         dmma884(c0, c1, a0, crow[j0 + q]);
                         dmma884(d0, d1, a1, crow[j0 + 4 + q]);
                     }
@@ -521,6 +616,62 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                 for (int e = tid; e < RL * LAC; e += NTHR) {
                     const int lr = e / LAC, c2 = e - lr * LAC, i = lr * C + crank;
                     if (i < Ks) Cloc[e] = Fp[c2 * ldp + i];
+                }
+                if (SYM) {
+                    // the other half of the symmetric product: T[i] += sum over MY rows j > i of P[j][i] C[j], for ALL i.
+                    // One warp per (8 output rows, 8 table columns); k runs over my local rows.  The partial rows go to
+                    // their owners (row i -> CTA i mod C) once every CTA has finished reading its copy of C.
+                    constexpr int MAXT = 8;
+                    const int nit = (Ks + 7) / 8, ntask = nit * nctl;
+                    double r0[MAXT], r1[MAXT];
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) {
+                        r0[t] = r1[t] = 0.0;
+                        const int task = warp + t * NWARP;
+                        if (task < ntask) {
+                            const int it = task / nctl, ctl = task - it * nctl;
+                            const int i = it * 8 + gq;
+                            const double* crow = Fp + (size_t)(ctl * 8 + gq) * ldp;
+                            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+                            int lr0 = (it * 8 - crank) / C;                 // first local row that can exceed the tile's rows
+                            if (lr0 < 0) lr0 = 0;
+                            for (; lr0 * C + crank < Ks; lr0 += 8) {
+                                const int lA = lr0 + q, jA = lA * C + crank, lB = lr0 + 4 + q, jB = lB * C + crank;
+                                const double a0 = (jA < Ks && jA > i && i < Ks) ? PR(lA)[i] : 0.0;
+                                const double a1 = (jB < Ks && jB > i && i < Ks) ? PR(lB)[i] : 0.0;
+                                const double b0 = (jA < Ks) ? crow[jA] : 0.0;
+                                const double b1 = (jB < Ks) ? crow[jB] : 0.0;
+                                dmma884(c0, c1, a0, b0);
+                                dmma884(d0, d1, a1, b1);
+                            }
+                            r0[t] = c0 + d0;
+                            r1[t] = c1 + d1;
+                        }
+                    }
+                    cl.sync();                                              // every CTA is done with C (Fp)
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) {
+                        const int task = warp + t * NWARP;
+                        if (task < ntask) {
+                            const int it = task / nctl, ctl = task - it * nctl;
+                            const int i = it * 8 + gq, col = ctl * 8 + 2 * q;
+                            if (i < Ks) {
+                                double* dst = cl.map_shared_rank(Fp + ((size_t)crank * RL + i / C) * LAC, (unsigned)(i % C));
+                                if (col < LAC) dst[col] = r0[t];
+                                if (col + 1 < LAC) dst[col + 1] = r1[t];
+                            }
+                        }
+                    }
+                    cl.sync();
+                    for (int e = tid; e < RL * LAC; e += NTHR) {
+                        const int lr = e / LAC, i = lr * C + crank;
+                        if (i < Ks) {
+                            double acc = Tloc[e];
+#pragma unroll
+                            for (int rr = 0; rr < C; ++rr) acc += Fp[(size_t)rr * RL * LAC + e];
+                            Tloc[e] = acc;
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -614,7 +765,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                 {
                     // P += (t G) t^T on my old rows (rank B on the tensor cores), then the new border rows / columns
                     const int nrt = ((Kn - crank + C - 1) / C + 7) / 8;
-                    tile_update<4>(Ploc, ldp, RL, nrt, 0, (Kn + 7) / 8, warp, lane,
+                    tile_update<4>(PR, PLEN, RL, nrt, 0, (Kn + 7) / 8, warp, lane,
                         [&](int lr, int k) -> double {
                             const int i = lr * C + crank;
                             if (k >= B || i >= Ks || (i >= pn && i < pn + B)) return 0.0;
@@ -623,23 +774,25 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                             for (int j2 = 0; j2 < B; ++j2) v += tb[j2 * ldp + i] * Gsh[j2 * B + k];
                             return v;
                         },
-                        [&](int k, int j) -> double { return (k < B) ? tb[k * ldp + j] : 0.0; }, no_limit);
+                        [&](int k, int j) -> double { return (k < B) ? tb[k * ldp + j] : 0.0; },
+                        [&](int rt) -> int { return SYM ? ((rt * 8 + 7) * C + crank) / 8 : (1 << 30); });
                     __syncthreads();
                     for (int e = tid; e < RL * B; e += NTHR) {       // border columns of my old rows: -t G
                         const int lr = e / B, b = e - lr * B, i = lr * C + crank;
-                        if (i < Ks && !(i >= pn && i < pn + B)) {
+                        if (i < Ks && !(i >= pn && i < pn + B) && (!SYM || i >= pn + B)) {
                             double v = 0.0;
 #pragma unroll
                             for (int j2 = 0; j2 < B; ++j2) v -= tb[j2 * ldp + i] * Gsh[j2 * B + b];
-                            Ploc[(size_t)lr * ldp + pn + b] = v;
+                            PR(lr)[pn + b] = v;
                         }
                     }
 #pragma unroll
                     for (int bi = 0; bi < B; ++bi) {                  // the new rows
                         const int i = pn + bi;
                         if (i % C == crank) {
-                            double* row = Ploc + (size_t)(i / C) * ldp;
-                            for (int j = tid; j < Kn; j += NTHR) {
+                            double* row = PR(i / C);
+                            const int jend = SYM ? i + 1 : Kn;
+                            for (int j = tid; j < jend; j += NTHR) {
                                 double x;
                                 if (j >= pn && j < pn + B) {
                                     x = Gsh[bi * B + (j - pn)];
@@ -735,8 +888,16 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                 for (int b = 0; b < B; ++b) {
                     if ((pos + b) % C == crank) {                      // the owner of row pos + b hands it to everyone
                         const int lr = (pos + b) / C;
-                        for (int j = tid; j < Ks; j += NTHR) store_all<C>(cl, &tb[b * ldp + j], Ploc[(size_t)lr * ldp + j]);
+                        const int jend = SYM ? pos + b + 1 : Ks;
+                        for (int j = tid; j < jend; j += NTHR) store_all<C>(cl, &tb[b * ldp + j], PR(lr)[j]);
                         if (tid < LAC) store_all<C>(cl, &vs[b * LAC + tid], Tloc[lr * LAC + tid]);
+                    }
+                }
+                if (SYM) {
+                    // lower triangle: P[j][pos + b] for j > pos + b sits in row j -- every CTA sends its rows' entries
+                    for (int e = tid; e < RL * B; e += NTHR) {
+                        const int lr = e / B, b = e - lr * B, j = lr * C + crank;
+                        if (j < Ks && j > pos + b) store_all<C>(cl, &tb[b * ldp + j], PR(lr)[pos + b]);
                     }
                 }
                 if (fw && lane == 0) {
@@ -758,7 +919,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                 __syncthreads();
                 {
                     const int nrt = ((Ks - crank + C - 1) / C + 7) / 8;
-                    tile_update<4>(Ploc, ldp, RL, nrt, 0, (Ks + 7) / 8, warp, lane,
+                    tile_update<4>(PR, PLEN, RL, nrt, 0, (Ks + 7) / 8, warp, lane,
                         [&](int lr, int k) -> double {
                             const int i = lr * C + crank;
                             if (k >= B || i >= Ks || (i >= pos && i < pos + B)) return 0.0;
@@ -767,17 +928,19 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                             for (int j2 = 0; j2 < B; ++j2) v -= tb[j2 * ldp + i] * Gsh[j2 * B + k];
                             return v;
                         },
-                        [&](int k, int j) -> double { return (k < B) ? tb[k * ldp + j] : 0.0; }, no_limit);
+                        [&](int k, int j) -> double { return (k < B) ? tb[k * ldp + j] : 0.0; },
+                        [&](int rt) -> int { return SYM ? ((rt * 8 + 7) * C + crank) / 8 : (1 << 30); });
                     __syncthreads();
                     for (int e = tid; e < RL * B; e += NTHR) {       // tombstone: zero columns ...
                         const int lr = e / B, b = e - lr * B, i = lr * C + crank;
-                        if (i < Ks) Ploc[(size_t)lr * ldp + pos + b] = 0.0;
+                        if (i < Ks && (!SYM || i > pos + b)) PR(lr)[pos + b] = 0.0;
                     }
 #pragma unroll
                     for (int b = 0; b < B; ++b) {                     // ... and rows
                         if ((pos + b) % C == crank) {
-                            double* row = Ploc + (size_t)((pos + b) / C) * ldp;
-                            for (int j = tid; j < Ks; j += NTHR) row[j] = 0.0;
+                            double* row = PR((pos + b) / C);
+                            const int jend = SYM ? pos + b + 1 : Ks;
+                            for (int j = tid; j < jend; j += NTHR) row[j] = 0.0;
                         }
                     }
                 }
@@ -873,7 +1036,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
         const int nrt = ((K - crank + C - 1) / C + 7) / 8;
         for (int lr = warp; lr * C + crank < K; lr += NWARP) {
             const int i = lr * C + crank, ci = cidx[i];
-            double* row = Ploc + (size_t)lr * ldp;
+            double* row = PR(lr);
             for (int j = lane; j <= i; j += 32) row[j] = Jp(ci, cidx[j]);
         }
         for (int j = tid; j < K; j += NTHR) hv[j] = hp(cidx[j]);
@@ -883,7 +1046,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
         int mb = 0;
         {   // the first pivot block goes to every CTA; later ones travel with the barrier that ends the previous step
             const int w0 = min(GW, K);
-            if (tid < GW * GW && pr < w0 && pc <= pr && pr % C == crank) store_all<C>(cl, &M8[tid], Ploc[(size_t)(pr / C) * ldp + pc]);
+            if (tid < GW * GW && pr < w0 && pc <= pr && pr % C == crank) store_all<C>(cl, &M8[tid], PR(pr / C)[pc]);
             cl.sync();
         }
         for (int k0 = 0; k0 < K; k0 += GW) {
@@ -915,12 +1078,12 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
             }
             hld += log(dprod);
             if (tid < w) rdg[k0 + tid] = rd8[tid];
-            if (mine) Ploc[(size_t)((k0 + pr) / C) * ldp + k0 + pc] = M8[tid];
+            if (mine) PR((k0 + pr) / C)[k0 + pc] = M8[tid];
             // panel L[j][k0 + b] = A[j][k0..] L_pp^-T for my rows j >= k1, handed to every CTA
             for (int lr = tid; lr < RL; lr += NTHR) {
                 const int j = lr * C + crank;
                 if (j >= k1 && j < K) {
-                    double* row = Ploc + (size_t)lr * ldp;
+                    double* row = PR(lr);
                     double x[GW];
 #pragma unroll
                     for (int b = 0; b < GW; ++b) x[b] = (b < w) ? row[k0 + b] : 0.0;
@@ -949,7 +1112,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                 hv[k0 + tid] = yv;
             }
             // trailing update of my rows >= k1, lower triangle (tile granularity), on the tensor cores
-            tile_update<8>(Ploc, ldp, RL, nrt, k1 / 8, (K + 7) / 8, warp, lane,
+            tile_update<8>(PR, PLEN, RL, nrt, k1 / 8, (K + 7) / 8, warp, lane,
                 [&](int lr, int k) -> double {
                     const int i = lr * C + crank;
                     return (i >= k1 && i < K) ? -Fp[k * ldp + i] : 0.0;
@@ -960,7 +1123,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
             if (k1 < K) {                                               // next pivot block -> every CTA's other pivot buffer
                 const int w1 = min(GW, K - k1);
                 if (tid < GW * GW && pr < w1 && pc <= pr && (k1 + pr) % C == crank)
-                    store_all<C>(cl, &M8base[(mb ^ 1) * GW * GW + tid], Ploc[(size_t)((k1 + pr) / C) * ldp + k1 + pc]);
+                    store_all<C>(cl, &M8base[(mb ^ 1) * GW * GW + tid], PR((k1 + pr) / C)[k1 + pc]);
             }
             cl.sync();                                                  // Fp is free again, the next pivot has arrived
             mb ^= 1;
@@ -981,7 +1144,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
                 double* spb = spart + bp * C * GW;
                 const int pr = tid / GW, pc = tid - pr * GW;
                 if (tid < GW * GW && pr < w && pc <= pr && (k0 + pr) % C == crank)
-                    store_all<C>(cl, &m8[tid], Ploc[(size_t)((k0 + pr) / C) * ldp + k0 + pc]);
+                    store_all<C>(cl, &m8[tid], PR((k0 + pr) / C)[k0 + pc]);
                 if (tid >= GW * GW && tid < GW * GW + GW) {
                     const int b = tid - GW * GW;
                     store_all<C>(cl, &spb[crank * GW + b], b < w ? sp[k0 + b] : 0.0);
@@ -1005,7 +1168,7 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
 #pragma unroll
                 for (int b = 0; b < GW; ++b) {
                     if (b < w && (k0 + b) % C == crank) {
-                        const double* row = Ploc + (size_t)((k0 + b) / C) * ldp;
+                        const double* row = PR((k0 + b) / C);
                         for (int j = tid; j < k0; j += NTHR) sp[j] += row[j] * o[b];
                     }
                 }
@@ -1059,11 +1222,11 @@ spike_slab_dsm_kernel(SpikeSlabArgs A, int RL, int ldp, int LAG, int XSZ, int FP
     cl.sync();                                          // no CTA exits while a peer may still address its shared memory
 }
 
-template <int B, int C>
+template <int B, int C, bool SYM>
 int launch_dsm_bc(const SpikeSlabArgs& A, cudaStream_t stream) {
-    const DsmGeom g = dsm_geom(A.N, B, C);
+    const DsmGeom g = dsm_geom(A.N, B, C, SYM);
     if (g.LAG < 1) return PYGLM_ERR_UNSUPPORTED;
-    PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_dsm_kernel<B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    PYGLM_CUDA(cudaFuncSetAttribute(spike_slab_dsm_kernel<B, C, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(A.n_loc * C, 1, 1);
     cfg.blockDim = dim3(NTHR, 1, 1);
@@ -1076,27 +1239,37 @@ int launch_dsm_bc(const SpikeSlabArgs& A, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PYGLM_CUDA(cudaLaunchKernelEx(&cfg, spike_slab_dsm_kernel<B, C>, A, g.RL, g.ldp, g.LAG, g.XSZ, g.FPN));
+    PYGLM_CUDA(cudaLaunchKernelEx(&cfg, spike_slab_dsm_kernel<B, C, SYM>, A, g.RL, g.ldp, g.LAG, g.XSZ, g.FPN, g.PSZ, g.TG));
     return PYGLM_OK;
+}
+
+// The cluster shapes that are built: 2 and 4 CTAs with the lower triangle of P (half the shared memory per neuron, so a
+// neuron fits fewer CTAs and more clusters are resident at once), 8 CTAs with full rows (the first version; what is left
+// when D is too large for the others).  pick_cluster: the smallest one whose shared memory holds the state.
+inline bool dsm_sym(int c) { return c != 8; }
+inline int pick_cluster(int N, int B) {
+    for (int c : {2, 4, 8})
+        if (dsm_geom(N, B, c, dsm_sym(c)).LAG >= 1) return c;
+    return 0;
 }
 
 template <int B>
 int launch_dsm_b(const SpikeSlabArgs& A, int csize, cudaStream_t stream) {
-    if (csize == 0) {
-        for (int c : {2, 4, 8})
-            if (dsm_geom(A.N, B, c).LAG >= 1) { csize = c; break; }
-    }
+    if (csize == 0) csize = pick_cluster(A.N, B);
     switch (csize) {
-        case 2: return launch_dsm_bc<B, 2>(A, stream);
-        case 4: return launch_dsm_bc<B, 4>(A, stream);
-        case 8: return launch_dsm_bc<B, 8>(A, stream);
+        case 2: return launch_dsm_bc<B, 2, true>(A, stream);
+        case 4: return launch_dsm_bc<B, 4, true>(A, stream);
+        case 8: return launch_dsm_bc<B, 8, false>(A, stream);
         default: return PYGLM_ERR_UNSUPPORTED;
     }
 }
 
 }  // namespace
 
+int choose_cluster(const SpikeSlabArgs& A);
+
 int spike_slab_dsm_launch(const SpikeSlabArgs& A, int csize, cudaStream_t stream) {
+    if (csize == 0) csize = choose_cluster(A);          // 0 again: launch_dsm_b falls back to the smallest shape that fits
     switch (A.B) {
         case 1: return launch_dsm_b<1>(A, csize, stream);
         case 2: return launch_dsm_b<2>(A, csize, stream);
@@ -1109,9 +1282,9 @@ int spike_slab_dsm_launch(const SpikeSlabArgs& A, int csize, cudaStream_t stream
 namespace {
 // Clusters of c CTAs with the kernel's shared-memory footprint that the device holds at once (GPC granularity: 13-14
 // clusters of 8 on a B200, not 148 / 8); 0 when the query fails.
-template <int B, int C>
+template <int B, int C, bool SYM>
 int dsm_active_clusters(const DsmGeom& g) {
-    if (cudaFuncSetAttribute(spike_slab_dsm_kernel<B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(spike_slab_dsm_kernel<B, C, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -1127,7 +1300,7 @@ int dsm_active_clusters(const DsmGeom& g) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, spike_slab_dsm_kernel<B, C>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, spike_slab_dsm_kernel<B, C, SYM>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -1136,41 +1309,55 @@ int dsm_active_clusters(const DsmGeom& g) {
 
 template <int B>
 int dsm_active_clusters_b(int N, int c) {
-    const DsmGeom g = dsm_geom(N, B, c);
+    const DsmGeom g = dsm_geom(N, B, c, dsm_sym(c));
     switch (c) {
-        case 2: return dsm_active_clusters<B, 2>(g);
-        case 4: return dsm_active_clusters<B, 4>(g);
-        default: return dsm_active_clusters<B, 8>(g);
+        case 2: return dsm_active_clusters<B, 2, true>(g);
+        case 4: return dsm_active_clusters<B, 4, true>(g);
+        default: return dsm_active_clusters<B, 8, false>(g);
     }
 }
-
 }  // namespace
 
-bool spike_slab_dsm_preferred(const SpikeSlabArgs& A) {
-    if (A.B < 1 || A.B > 4 || A.N * A.B + 1 < 24) return false;
-    int c = 0;
-    for (int cc : {2, 4, 8})
-        if (dsm_geom(A.N, A.B, cc).LAG >= 1) { c = cc; break; }
-    if (c == 0) return false;
-    // Measured at cfg3 (D = 401, 8 CTAs per neuron; profiles/r02l_probe_scan_dsm.log): a cluster finishes a neuron in
-    // 0.95 ms against 2.4-3.2 ms for one CTA with P in L2, but a B200 holds only 13-14 such clusters at once, so 13 / 25 /
-    // 50 neurons take 0.97 / 1.83 / 3.6 ms against 2.34 / 2.40 / 3.19 ms.  The cluster kernel is therefore preferred
-    // while the local neurons fit PYGLM_SS_DSM_MAX_WAVES (default 2) waves of resident clusters -- the scan blocks of
-    // the 8-GPU runs -- and the single-CTA kernel otherwise.
+// Which cluster shape, if any, should run n_loc neurons: 0 = none (one CTA per neuron wins).  Estimated time = waves of
+// resident clusters x the per-cluster time measured at cfg3's shape (D = 401, K ~ 250; profiles/r02r_probe_scan_dsm.log):
+// 0.90 ms for 8 CTAs with full rows (13-14 resident), 1.40 ms for 4 CTAs with the lower triangle (~30 resident; its
+// lookahead table is shorter), ~2 ms for 2 CTAs; against 2.4 / 3.1 / 5.0 ms for <= 100 / <= 148 / 200 single-CTA neurons.
+// The ratios, not the absolute values, decide; PYGLM_SS_DSM_MAX_WAVES caps the waves a cluster shape may need (default 2).
+int choose_cluster(const SpikeSlabArgs& A) {
+    if (A.B < 1 || A.B > 4 || A.N * A.B + 1 < 24) return 0;
     static int max_waves = -1;
     if (max_waves < 0) { const char* e = getenv("PYGLM_SS_DSM_MAX_WAVES"); max_waves = e ? atoi(e) : 2; }
-    static int cap_key = -1, cap = 0;
-    const int key = (A.N * 8 + A.B) * 16 + c;
+    static int cap_key = -1, caps[3] = {0, 0, 0};
+    const int shapes[3] = {2, 4, 8};
+    const double t_shape[3] = {2.0, 1.4, 0.9};
+    const int key = A.N * 8 + A.B;
     if (key != cap_key) {
-        switch (A.B) {
-            case 1: cap = dsm_active_clusters_b<1>(A.N, c); break;
-            case 2: cap = dsm_active_clusters_b<2>(A.N, c); break;
-            case 3: cap = dsm_active_clusters_b<3>(A.N, c); break;
-            default: cap = dsm_active_clusters_b<4>(A.N, c); break;
+        for (int k = 0; k < 3; ++k) {
+            const int c = shapes[k];
+            caps[k] = 0;
+            if (dsm_geom(A.N, A.B, c, dsm_sym(c)).LAG < 1) continue;
+            switch (A.B) {
+                case 1: caps[k] = dsm_active_clusters_b<1>(A.N, c); break;
+                case 2: caps[k] = dsm_active_clusters_b<2>(A.N, c); break;
+                case 3: caps[k] = dsm_active_clusters_b<3>(A.N, c); break;
+                default: caps[k] = dsm_active_clusters_b<4>(A.N, c); break;
+            }
         }
         cap_key = key;
     }
-    return cap > 0 && A.n_loc <= max_waves * cap;
+    const int w1 = (A.n_loc + 147) / 148;
+    double best = (A.n_loc <= 100) ? 2.4 : (w1 == 1 ? 3.1 : 2.5 * w1);
+    int pick = 0;
+    for (int k = 0; k < 3; ++k) {
+        if (caps[k] <= 0) continue;
+        const int waves = (A.n_loc + caps[k] - 1) / caps[k];
+        if (waves > max_waves) continue;
+        const double t = waves * t_shape[k];
+        if (t < best) { best = t; pick = shapes[k]; }
+    }
+    return pick;
 }
+
+bool spike_slab_dsm_preferred(const SpikeSlabArgs& A) { return choose_cluster(A) != 0; }
 
 }  // namespace pyglm_ss

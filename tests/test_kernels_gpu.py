@@ -485,10 +485,11 @@ def run_spike_slab(K, N, B, J_l, h_l, hyper_list, a0, perm, us, z):
     return a.cpu().numpy().astype(bool), W.cpu().numpy(), bias.cpu().numpy(), lo.cpu().numpy(), ml.cpu().numpy()
 
 
-@pytest.fixture(params=["1", "80", "88", "84"], ids=["one-cta", "cluster", "cluster8", "cluster4"])
+@pytest.fixture(params=["1", "80", "88", "84", "82"], ids=["one-cta", "cluster", "cluster8-full", "cluster4-tri", "cluster2-tri"])
 def ss_kernel(request, monkeypatch):
     """Every spike-and-slab test runs on the one-CTA-per-neuron kernel (spike_slab.cu) and on the cluster kernel with P in
-    distributed shared memory (spike_slab_dsm.cu: smallest cluster that fits, 8 CTAs, 4 CTAs)."""
+    distributed shared memory (spike_slab_dsm.cu): the smallest cluster that fits, 8 CTAs with full rows of P, 4 and 2
+    CTAs with its lower triangle."""
     monkeypatch.setenv("PYGLM_SS_VARIANT", request.param)
     return request.param
 
@@ -540,8 +541,8 @@ def test_spike_slab_random_vs_oracle(K, N, B, T, n_loc, seed, ss_kernel):
     neuron-specific, non-isotropic priors as the NIW network step produces them (models.py:232-236).  The last case
     (D = 181, active sets of ~90 coordinates) drives the blocked inverse / Cholesky through many pivot blocks and a
     partial last block."""
-    if ss_kernel == "84" and N * B > 280:
-        pytest.skip("D = 401 does not fit the shared memory of a 4-CTA cluster")
+    if ss_kernel == "82" and N * B > 280:
+        pytest.skip("D = 401 does not fit the shared memory of a 2-CTA cluster")
     rng = np.random.default_rng(seed)
     Y = spikes(T, N, seed=seed, rate=0.1)
     X = O.convolve_with_basis(Y, O.cosine_basis(B, 20) / 20).reshape(T, N * B)
