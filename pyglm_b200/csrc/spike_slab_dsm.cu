@@ -85,32 +85,38 @@ __device__ __forceinline__ bool chol8(double* M8, int lane, int w) {
 }
 
 // P[lr][j] += sum_{k < KD} a(lr, k) b(k, j) on my rows (FP64 tensor cores, DMMA.8x8x4): row tiles of 8 local rows, column
-// tiles [ct0, ct1) of 8, row tile rt stopping after column tile ctlast(rt).  A warp keeps its A fragment and walks a
-// strided subset of the column tiles.  a(lr, k) must return 0 for rows that are not to be touched; columns beyond the
+// tiles [ct0, ct1) of 8, row tile rt stopping after column tile ctlast(rt) (lower-triangular storage: the rows of a tile
+// end at different columns, rowlen() bounds each lane's stores).  Work items are (row tile, chunk of U column tiles),
+// dealt round-robin to the warps over the FLATTENED list, so that a triangular update is balanced too; the U tiles of an
+// item are independent DMMA chains.  a(lr, k) must return 0 for rows that are not to be touched; columns beyond the
 // matrix receive garbage that nobody reads.
 template <int KD, class RP, class RN, class AF, class BF, class CL>
 __device__ __forceinline__ void tile_update(RP rowptr, RN rowlen, int RL, int nrt, int ct0, int ct1, int warp, int lane,
                                             AF afrag, BF bfrag, CL ctlast) {
     const int g = lane >> 2, q = lane & 3;
-    const int ngrp = (nrt >= NWARP) ? 1 : NWARP / nrt;
-    constexpr int U = 4;                                  // column tiles in flight per warp (independent DMMA chains)
-    for (int task = warp; task < nrt * ngrp; task += NWARP) {
-        const int rt = task / ngrp, cgq = task - rt * ngrp;
+    constexpr int U = 4;                                  // column tiles in flight per item
+    int base = 0;                                         // items before row tile rt in the flattened list
+    for (int rt = 0; rt < nrt; ++rt) {
+        const int cend = min(ct1, ctlast(rt) + 1);
+        const int nch = (cend > ct0) ? (cend - ct0 + U - 1) / U : 0;
+        int ch = (warp - base % NWARP + NWARP) % NWARP;   // my first chunk of this row tile
+        base += nch;
+        if (ch >= nch) continue;
         const int lr = rt * 8 + g;
         const double a0 = afrag(lr, q);
         const double a1 = (KD == 8) ? afrag(lr, 4 + q) : 0.0;
-        const int cend = min(ct1, ctlast(rt) + 1);
         const bool rowok = lr < RL;
         double* rowp = rowptr(rowok ? lr : 0) + 2 * q;
         const int rlen = rowlen(rowok ? lr : 0);           // allocated entries of the row (full rows: the pitch)
-        for (int ct = ct0 + cgq; ct < cend; ct += U * ngrp) {
+        for (; ch < nch; ch += NWARP) {
+            const int ct = ct0 + ch * U;
             double2 c[U];
             double b0[U], b1[U];
             bool ok[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int j = (ct + u * ngrp) * 8;
-                const bool in = ct + u * ngrp < cend;
+                const int j = (ct + u) * 8;
+                const bool in = ct + u < cend;
                 ok[u] = in && rowok && (j + 2 * q + 1 < rlen);
                 c[u] = ok[u] ? *reinterpret_cast<double2*>(rowp + j) : make_double2(0.0, 0.0);
                 b0[u] = in ? bfrag(q, j + g) : 0.0;
@@ -124,7 +130,7 @@ __device__ __forceinline__ void tile_update(RP rowptr, RN rowlen, int RL, int nr
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (ok[u]) *reinterpret_cast<double2*>(rowp + (ct + u * ngrp) * 8) = c[u];
+                if (ok[u]) *reinterpret_cast<double2*>(rowp + (ct + u) * 8) = c[u];
         }
     }
 }
