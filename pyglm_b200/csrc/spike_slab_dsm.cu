@@ -1351,6 +1351,9 @@ int choose_cluster(const SpikeSlabArgs& A) {
         }
         cap_key = key;
     }
+    // small problems (cfg2: D = 82) are barrier-bound whatever the cluster size: there the shapes cost the same per
+    // neuron and the smallest one that fits wins by needing the fewest SMs
+    const bool small = A.N * A.B + 1 <= 200;
     const int w1 = (A.n_loc + 147) / 148;
     double best = (A.n_loc <= 100) ? 2.4 : (w1 == 1 ? 3.1 : 2.5 * w1);
     int pick = 0;
@@ -1358,7 +1361,7 @@ int choose_cluster(const SpikeSlabArgs& A) {
         if (caps[k] <= 0) continue;
         const int waves = (A.n_loc + caps[k] - 1) / caps[k];
         if (waves > max_waves) continue;
-        const double t = waves * t_shape[k];
+        const double t = waves * (small ? 1.0 : t_shape[k]);
         if (t < best) { best = t; pick = shapes[k]; }
     }
     return pick;
