@@ -21,11 +21,11 @@ def _free_port():
     return p
 
 
-def _chain(comm, shard, n_sweeps=3, gram="auto", prior=None):
+def _chain(comm, shard, n_sweeps=3, gram="auto", prior=None, N=10, T=5000):
     from pyglm_b200 import networks
     from pyglm_b200.models import SparseBernoulliGLM
     from pyglm_b200.utils.basis import cosine_basis
-    N, B, L, T = 10, 2, 20, 5000
+    B, L = 2, 20
     basis = cosine_basis(B, L) / L
     Y = (np.random.default_rng(3).random((T, N)) < 0.08).astype(np.float64)
     # a prior with latent state is built from a rank-dependent seed: the model has to hand out rank 0's
@@ -42,16 +42,17 @@ def _chain(comm, shard, n_sweeps=3, gram="auto", prior=None):
     return m.adjacency, m.weights, m.biases, np.array(lls)
 
 
-def _worker(rank, world, port, shard, out, gram="auto", prior=None):
+def _worker(rank, world, port, shard, out, gram="auto", prior=None, N=10, T=5000, peer="1"):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["PYGLM_PEER_EXCHANGE"] = peer
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from pyglm_b200.distributed import Comm
-        A, W, b, lls = _chain(Comm(), shard, gram=gram, prior=prior)
+        A, W, b, lls = _chain(Comm(), shard, gram=gram, prior=prior, N=N, T=T)
         if rank == 0:
             np.savez(out, A=A, W=W, b=b, lls=lls)
     finally:
@@ -107,3 +108,24 @@ def test_two_gpu_chain_with_stateful_network_prior(tmp_path, prior):
     assert np.array_equal(g["A"], A0)
     np.testing.assert_allclose(g["W"], W0, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(g["lls"], lls0, rtol=1e-9)
+
+
+@pytest.mark.parametrize("peer", ["1", "0"], ids=["peer-memory", "nccl"])
+def test_two_gpu_time_sharded_cluster_scan_and_both_exchange_paths(tmp_path, peer):
+    """N = 40, B = 2 (D = 81): large enough for the CLUSTER scan kernel (csrc/spike_slab_dsm.cu) on both the single-GPU
+    run and the 20-neuron scan blocks of the two ranks, with the tensor-core Gram time-sharded.  Run once with the
+    exchanges as our own kernels over peer-mapped memory (reduce-scatter fused into the finalize pass, state rows pushed
+    over NVLink) and once with the NCCL collectives: both must reproduce the single-GPU chain."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from pyglm_b200.distributed import Comm
+    N, T = 40, 20000
+    A0, W0, b0, lls0 = _chain(Comm(), "neuron", gram="tc", N=N, T=T)
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_worker, args=(2, _free_port(), "time", out, "tc", None, N, T, peer), nprocs=2, join=True)
+    g = np.load(out)
+    assert np.array_equal(g["A"], A0)
+    np.testing.assert_allclose(g["W"], W0, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(g["b"], b0, rtol=1e-8)
+    np.testing.assert_allclose(g["lls"], lls0, rtol=1e-10)
