@@ -353,7 +353,13 @@ def main():
     n_loc = eng.psi_hi - eng.psi_lo
     hyp = model._stacked_hypers()
     barrier()
-    eng.profile = {}
+    # Large single-GPU models sweep as two neuron groups on two streams (engine._sweep_overlapped): the phases of the
+    # groups overlap, so per-phase events inside that region would not add up.  `value` is then timed on the overlapped
+    # sweeps as they run in production, and the per-kernel times (and the roofline of the Gram kernel) come from a
+    # second pass of the same number of sweeps with the overlap switched off -- same kernels, same chain, one block.
+    overlapped = eng._overlap_groups([ds]) is not None
+    if not overlapped:
+        eng.profile = {}
     coll0 = eng.comm.collective_calls
     ev0.record()
     for _ in range(steps):
@@ -362,6 +368,20 @@ def main():
     coll = (eng.comm.collective_calls - coll0) / float(steps)
     barrier()
     dev_ms = ev0.elapsed_time(ev1) / steps
+    serial_ms = None
+    if overlapped:
+        eng.overlap = False
+        for _ in range(2):                               # builds / verifies the one-block plan, refills the pipeline
+            A, W, b = eng.sweep([ds], A, W, b, hyp)
+        barrier()
+        eng.profile = {}
+        ev0.record()
+        for _ in range(steps):
+            A, W, b = eng.sweep([ds], A, W, b, hyp)
+        ev1.record()
+        barrier()
+        serial_ms = ev0.elapsed_time(ev1) / steps
+        eng.overlap = True
     kern_ms = eng.phase_ms()
     eng.profile = None
     clocks = sampler.stop() if rank == 0 else None
@@ -420,6 +440,9 @@ def main():
                 par += "; NCCL collectives (%.2f per sweep)" % coll
         else:
             par = "%s-sharded x%d" % (eng.shard, world)
+            if overlapped:
+                par = ("one GPU, two neuron groups on two streams: the scan of one group overlaps the psi / PG / Gram of "
+                       "the other (dynamic item queue in the Gram kernel)")
             if world > 1:
                 par += ("; state rows pushed over NVLink by our own kernel, %.2f torch.distributed collectives per sweep"
                         % coll) if eng.peer is not None else "; NCCL all-gather (%.2f collectives per sweep)" % coll
@@ -446,6 +469,11 @@ def main():
                          note="outside every timed region"),
             clocks=clocks,
         )
+        if overlapped:
+            line["overlap"] = dict(groups=2, one_block_ms_per_step=serial_ms,
+                                   note="ms_per_step / value / e2e: overlapped sweeps; kernels_ms, roofline, pg_roofline: "
+                                        "a second pass of the same sweeps with the overlap off (one block, one stream), "
+                                        "where each kernel has the GPU to itself")
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, args.cpu_baseline_neurons)
         emit(line)

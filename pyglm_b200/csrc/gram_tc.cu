@@ -29,6 +29,7 @@
 // Work item = (pair tile, neuron tile, time chunk <= 16384 bins); persistent CTAs stride over the item list.
 #include "common.cuh"
 #include <cuda.h>
+#include <mutex>
 #include <stdlib.h>
 
 namespace {
@@ -185,6 +186,8 @@ struct TcItems {
     const int* tiles;       // streaming kernel: (i block, j block) of every 8 x 16 pair tile, n_mtiles entries (device)
     int D;                  // streaming kernel: columns of the design (pairs (i, j), j <= i < D)
     int Dp;                 // streaming kernel: rows per 32-bin block of the tiled fixed-point design (D rounded up to 16)
+    int* ticket;            // gram_tcm_kernel: device counter of the dynamic item queue (zeroed before the launch), or
+                            // nullptr for the static round-robin schedule above
 };
 
 // Item schedule.  CTAs are grouped n_ntiles at a time; in round k group q works on (pair tile, time chunk) number
@@ -206,6 +209,50 @@ __device__ __forceinline__ TcWork tc_work(const TcItems& it, int round) {
 // neurons (MMA N) of a neuron tile: the last tile may be narrower, in steps of 16
 __device__ __forceinline__ int tc_tile_n(const TcItems& it, int ntile) {
     return min(it.nt, (it.n_valid - ntile * it.nt + 15) / 16 * 16);
+}
+
+// Dynamic item queue (gram_tcm_kernel): ticket t = ((chunk * n_mtiles + mtile) * n_ntiles + ntile), taken from a device
+// counter.  The sums go to Jint through integer atomics, so WHICH CTA works on an item changes nothing in the result;
+// what the queue buys is that a CTA which starts late -- its SM was still running another stream's kernel (the
+// spike-and-slab scan of the other neuron group, engine.py) -- simply takes fewer items instead of holding back the
+// whole launch with its fixed share.  Neighbouring tickets are the neuron tiles of one (pair tile, chunk), so the CTAs
+// that draw them at about the same time still read the same rows of the design from L2.
+__device__ __forceinline__ TcWork tc_work_ticket(const TcItems& it, int t) {
+    const long long total = (long long)it.n_mtiles * it.n_chunks * it.n_ntiles;
+    TcWork w;
+    w.valid = t >= 0 && (long long)t < total;
+    const int lin = t / it.n_ntiles;
+    w.ntile = t - lin * it.n_ntiles;
+    w.mtile = lin % it.n_mtiles;
+    w.chunk = lin / it.n_mtiles;
+    return w;
+}
+constexpr int TM_RING = 4;             // tickets the producer warp may run ahead of the slowest role of its CTA
+// Producer warp: draw the ticket of this round and publish it to the other 13 warps through a ring in shared memory.
+__device__ __forceinline__ TcWork tm_draw(const TcItems& it, int round, int lane, int* ring, uint32_t rfull0, uint32_t rempty0) {
+    if (it.ticket == nullptr) return tc_work(it, round);
+    const int slot = round % TM_RING;
+    const uint32_t par = (uint32_t)(round / TM_RING) & 1u;
+    mbar_wait(rempty0 + 8 * slot, par ^ 1u);                 // every other warp has read the slot's previous ticket
+    int t = 0;
+    if (lane == 0) {
+        t = atomicAdd(it.ticket, 1);
+        *reinterpret_cast<volatile int*>(ring + slot) = t;
+        mbar_arrive(rfull0 + 8 * slot);                      // release: the store above is visible to the waiters
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    return tc_work_ticket(it, t);
+}
+// The other warps: wait for the ticket of this round.
+__device__ __forceinline__ TcWork tm_take(const TcItems& it, int round, int lane, const int* ring, uint32_t rfull0, uint32_t rempty0) {
+    if (it.ticket == nullptr) return tc_work(it, round);
+    const int slot = round % TM_RING;
+    const uint32_t par = (uint32_t)(round / TM_RING) & 1u;
+    mbar_wait(rfull0 + 8 * slot, par);
+    int t = *reinterpret_cast<const volatile int*>(ring + slot);
+    t = __shfl_sync(0xffffffffu, t, 0);                      // warp-uniform for the compiler, and every lane has read
+    if (lane == 0) mbar_arrive(rempty0 + 8 * slot);
+    return tc_work_ticket(it, t);
 }
 
 template <int S, bool MC>
@@ -685,8 +732,9 @@ gram_tcm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     constexpr int RW_OFF = XQ_OFF + TS_XQ_BYTES;
     constexpr int STAGE = (RW_OFF + TS_RW_BYTES + 1023) & ~1023;
     const uint32_t stage_tx = (uint32_t)(S * B_SLICE + TS_XQ_BYTES + TS_RW_BYTES);
-    __shared__ __align__(8) uint64_t bars[2 * TM_STAGES + 6];
+    __shared__ __align__(8) uint64_t bars[2 * TM_STAGES + 6 + 2 * TM_RING];
     __shared__ uint32_t tmem_slot;
+    __shared__ int ring[TM_RING];
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -694,12 +742,14 @@ gram_tcm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     const uint32_t fin0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TM_STAGES]);
     const uint32_t afull0 = smem_u32(&bars[2 * TM_STAGES]), aempty0 = smem_u32(&bars[2 * TM_STAGES + 2]);
     const uint32_t tfull = smem_u32(&bars[2 * TM_STAGES + 4]), tempty = smem_u32(&bars[2 * TM_STAGES + 5]);
+    const uint32_t rfull0 = smem_u32(&bars[2 * TM_STAGES + 6]), rempty0 = smem_u32(&bars[2 * TM_STAGES + 6 + TM_RING]);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TM_STAGES; ++s) { mbar_init(fin0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int h = 0; h < 2; ++h) { mbar_init(afull0 + 8 * h, TS_BUILD_WARPS / 2); mbar_init(aempty0 + 8 * h, 1); }
         mbar_init(tfull, 1);
         mbar_init(tempty, 4);
+        for (int s = 0; s < TM_RING; ++s) { mbar_init(rfull0 + 8 * s, 1); mbar_init(rempty0 + 8 * s, TS_THREADS / 32 - 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -719,7 +769,7 @@ gram_tcm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         for (int round = 0;; ++round) {
-            const TcWork wk = tc_work(it, round);
+            const TcWork wk = tm_draw(it, round, lane, ring, rfull0, rempty0);
             if (!wk.valid) break;
             const int kb0 = wk.chunk * it.blocks_per_chunk;
             const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
@@ -752,7 +802,7 @@ gram_tcm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0, tphase = 0, aphase = 0;
         for (int round = 0;; ++round) {
-            const TcWork wk = tc_work(it, round);
+            const TcWork wk = tm_take(it, round, lane, ring, rfull0, rempty0);
             if (!wk.valid) break;
             const int n_mma = tc_tile_n(it, wk.ntile);
             const uint32_t id_uu = tc_idesc(0, 0, n_mma), id_us = tc_idesc(0, 1, n_mma);
@@ -799,7 +849,7 @@ gram_tcm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         const int quarter = warp & 3;
         uint32_t tphase = 0;
         for (int round = 0;; ++round) {
-            const TcWork wk = tc_work(it, round);
+            const TcWork wk = tm_take(it, round, lane, ring, rfull0, rempty0);
             if (!wk.valid) break;
             const int ntile = wk.ntile;
             const int n_mma = tc_tile_n(it, ntile);
@@ -847,7 +897,7 @@ gram_tcm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0, aphase = 0;
         for (int round = 0;; ++round) {
-            const TcWork wk = tc_work(it, round);
+            const TcWork wk = tm_take(it, round, lane, ring, rfull0, rempty0);
             if (!wk.valid) break;
             const int kb0 = wk.chunk * it.blocks_per_chunk;
             const int kb1 = min(it.n_blocks, kb0 + it.blocks_per_chunk);
@@ -1262,6 +1312,29 @@ int ts_launch(const uint32_t* xq, const unsigned long long* rw, const uint8_t* O
         const int tm_stage = (S * TM_NT_MAX * TC_BK + TS_XQ_BYTES + TS_RW_BYTES + 1023) & ~1023;
         const int tm_smem = TM_STAGES * tm_stage + 1024;
         PYGLM_CUDA(cudaFuncSetAttribute(gram_tcm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem));
+        // dynamic item queue (PYGLM_TC_DYNAMIC=0: the static round-robin schedule): one CTA per SM, each drawing
+        // (pair tile, chunk, neuron tile) tickets from a device counter.  The counter comes from a small per-device
+        // pool used round-robin, so launches in flight on different streams never share one.
+        static int dyn = -1;
+        if (dyn < 0) { const char* e = getenv("PYGLM_TC_DYNAMIC"); dyn = e ? atoi(e) : 1; }
+        if (dyn) {
+            constexpr int POOL = 256, MAXDEV = 64;
+            static std::mutex mu;
+            static int* pool[MAXDEV] = {};
+            static unsigned next[MAXDEV] = {};
+            int* ctr = nullptr;
+            if (dev >= 0 && dev < MAXDEV) {
+                std::lock_guard<std::mutex> lock(mu);
+                if (!pool[dev]) PYGLM_CUDA(cudaMalloc(&pool[dev], POOL * sizeof(int)));
+                ctr = pool[dev] + (next[dev]++ % POOL);
+            }
+            const long long total = pairs * it.n_ntiles;
+            if (ctr && total < (1LL << 30)) {
+                PYGLM_CUDA(cudaMemsetAsync(ctr, 0, sizeof(int), stream));
+                sched.ticket = ctr;
+                sched.n_ctas = (int)(total < sms ? total : sms);
+            }
+        }
         gram_tcm_kernel<S><<<sched.n_ctas, TS_THREADS, tm_smem, stream>>>(mx, mo, rw, Jint, sched);
     } else {
         PYGLM_CUDA(cudaFuncSetAttribute(gram_tcs_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1386,7 +1459,7 @@ static int gram_tc_mma_impl(const unsigned char* Zs, const unsigned char* Os, in
     it.tiles = nullptr; it.D = D; it.Dp = 0;
     static int multicast = -1;
     if (multicast < 0) { const char* e = getenv("PYGLM_TC_MULTICAST"); multicast = e ? atoi(e) : 1; }
-    it.multicast = multicast; it.n_ctas = 0;
+    it.multicast = multicast; it.n_ctas = 0; it.ticket = nullptr;
     if (max_ctas < 0) { it.multicast = 0; max_ctas = (max_ctas == -1) ? 0 : -max_ctas; }   // measurement hook
     PYGLM_CUDA(cudaMemsetAsync(Jint, 0, sizeof(long long) * (size_t)n_valid * (size_t)ldjint, stream));
     switch (S) {
@@ -1467,7 +1540,7 @@ extern "C" int pyglm_gram_tc_mma_stream(const unsigned int* xq, const unsigned l
     TcItems it;
     it.M = g[0]; it.Mpad = g[1]; it.Npad = (int)g[3]; it.nt = (int)g[4]; it.n_ntiles = (int)g[5];
     it.n_chunks = (int)g[6]; it.blocks_per_chunk = (int)g[7]; it.n_blocks = (int)(g[2] / TC_BK);
-    it.n_mtiles = n_tiles; it.n_valid = n_valid; it.ldj = ldjint; it.probe = 0; it.multicast = 0; it.n_ctas = 0;
+    it.n_mtiles = n_tiles; it.n_valid = n_valid; it.ldj = ldjint; it.probe = 0; it.multicast = 0; it.n_ctas = 0; it.ticket = nullptr;
     it.tiles = tiles; it.D = D; it.Dp = (D + 15) / 16 * 16;
     PYGLM_CHECK_ARG((long long)S * it.n_blocks * it.Npad < (1LL << 31) && (g[2] / 32) * it.Dp < (1LL << 31),
                     "pyglm_gram_tc_mma_stream: problem too large for 32-bit TMA coordinates");

@@ -121,6 +121,16 @@ class GibbsEngine(object):
         self._pending = None
         # Optional on-device sample statistics (DeviceMoments); None = off.
         self.moments = None
+        # Opt-in (PYGLM_OVERLAP=1 or .overlap = True): single-GPU sweeps of >= OVERLAP_MIN_N neurons run as two neuron
+        # groups on two streams (see _sweep_overlapped), the scan of one group sharing the GPU with the psi / PG / Gram of
+        # the other.  Off by default: measured at cfg3 it only pays while the chain is sparse (16.0 against 18.5 ms per
+        # sweep over the first sweeps); at the equilibrium density the scan is L2-bandwidth bound, a group's single wave
+        # (3.8 ms, stretched by the co-running psi / PG streams) costs as much as its share of the one-block scan
+        # (6.5 ms for 1.35 waves, whose tail wave runs with less contention), and both modes take 19.3-19.8 ms
+        # (profiles/r02ac_sweep_times.log).
+        self.overlap = os.environ.get("PYGLM_OVERLAP", "0") == "1"
+        self.overlap_min_n = self.OVERLAP_MIN_N
+        self._ovl = None
         # Exchange steps over peer-mapped memory with our own kernels (distributed.PeerExchange) when the ranks are GPUs
         # of one NVLink domain; otherwise (gloo CPU tests, PYGLM_PEER_EXCHANGE=0, allocation failure) the NCCL / gloo
         # collectives of Comm.  All ranks decide alike (the constructor is collective).
@@ -225,7 +235,11 @@ class GibbsEngine(object):
             return True
         return False if fits else None
 
-    def _tc_build(self, ds, n, digits):
+    @staticmethod
+    def _tc_key(n, tag=None):
+        return ("tc_plan", n) if tag is None else ("tc_plan", n, tag)
+
+    def _tc_build(self, ds, n, digits, share=None):
         stream = self._tc_stream(ds, n, digits)
         if stream is None:
             return None
@@ -244,20 +258,28 @@ class GibbsEngine(object):
                 elif rows != n:
                     plan.Jint = torch.zeros(rows, plan.geom["Mpad"], dtype=torch.int64, device=self.K.device)
                 return plan
-            return self.K.gram_tc_plan(ds.Xp, self.D, n, digits, stream=stream)
+            if share is not None and (share.S, share.stream) != (digits, bool(stream)):
+                share = None
+            return self.K.gram_tc_plan(ds.Xp, self.D, n, digits, stream=stream, share=share)
         except ValueError:
             return None                  # signed design: the digits of Z assume x >= 0
 
-    def _tc_plan(self, ds, n):
-        """The dataset's tensor-core Gram plan for n local neurons, or None when the FP64 kernel should run."""
+    def _tc_plan(self, ds, n, tag=None):
+        """The dataset's tensor-core Gram plan for n local neurons, or None when the FP64 kernel should run.
+        tag: neuron group of the overlapped single-GPU sweep (its own per-sweep buffers, the operand shared)."""
         if self.gram_mode == "fp64" or not hasattr(self.K, "gram_tc_plan"):
             return None
-        key = ("tc_plan", n)
+        key = self._tc_key(n, tag)
         if key not in ds.buffers:
             M = self.D * (self.D + 1) // 2
             T_eff = ds.T_global / self.comm.world if self._time_sharded() else ds.T
             want = self.gram_mode == "tc" or float(M) * T_eff * n >= self.TC_MIN_WORK
-            plan = self._tc_build(ds, n, self.gram_digits) if want else None
+            share = None
+            if tag is not None:
+                share = next((v for k, v in ds.buffers.items() if k[0] == "tc_plan" and v is not None), None)
+            plan = self._tc_build(ds, n, self.gram_digits, share=share) if want else None
+            if plan is not None:
+                plan.key = key
             if plan is None and self.gram_mode == "tc":
                 raise RuntimeError("gram='tc' needs a non-negative design and %.1f GB of free HBM"
                                    % (gram_tc_bytes(self.D, n, ds.T, self.gram_digits,
@@ -265,14 +287,14 @@ class GibbsEngine(object):
             ds.buffers[key] = plan
         return ds.buffers[key]
 
-    def _tc_verified(self, ds, omega, n, plan):
+    def _tc_verified(self, ds, omega, n, plan, tag=None):
         """First use of a plan: run it beside the FP64 kernel on the sweep's own omega and keep it only if the
         two agree to TC_ACCEPT on every lower-triangle entry; otherwise add a digit, then give up (FP64).  The
         deviation of the integer-digit product depends on the data (sparser trains -> smaller entries relative to
         the fixed-point scale), so it is measured, not assumed.  Time-sharded: what is compared are the COMPLETE
         Grams of each rank's neuron block after the reduce-scatter (the integer totals are the single-GPU ones, so
         the decision is too); the worst rank decides for all."""
-        key = ("tc_plan", n)
+        key = self._tc_key(n, tag)
         rows = max(self.scan_hi - self.scan_lo, 1) if self._time_sharded() else n
         J_ref = self._gram_fp64(ds, omega, n, self.K.zeros(rows, self.ldx, self.ldx))
         tril = torch.tril(torch.ones(self.D, self.D, dtype=torch.bool, device=J_ref.device))
@@ -297,6 +319,8 @@ class GibbsEngine(object):
             torch.cuda.empty_cache()
             if digits <= 5:
                 plan = self._tc_build(ds, n, digits)
+                if plan is not None:
+                    plan.key = key
         if plan is None and self.gram_mode == "tc":
             raise RuntimeError("gram='tc': the integer-digit Gram deviates from FP64 by more than %.1e" % self.TC_ACCEPT)
         ds.buffers[key] = plan
@@ -399,17 +423,17 @@ class GibbsEngine(object):
                           "falling back to the FP64 kernel for this data set" % (worst, limit))
             if self.gram_mode == "tc":
                 raise RuntimeError("gram='tc': spot check of the integer-digit Gram failed (%.2e)" % worst)
-            ds.buffers[("tc_plan", n)] = None
+            ds.buffers[getattr(plan, "key", ("tc_plan", n))] = None
             self._pending = None
 
-    def weighted_gram(self, ds, omega, n, J):
+    def weighted_gram(self, ds, omega, n, J, tag=None):
         """J (rows of the scan block) = this dataset's weighted Gram.  Neuron-sharded / single GPU: n = local
         neurons, J has n rows.  Time-sharded: n = N, the slab's partial sums of ALL neurons are reduce-scattered
         over the neuron axis (exact int64 sums on the tensor-core path, FP64 otherwise) and J receives the complete
         Grams of this rank's neuron block."""
-        plan = self._tc_plan(ds, n)
+        plan = self._tc_plan(ds, n, tag)
         if plan is not None and not plan.verified:
-            plan = self._tc_verified(ds, omega, n, plan)
+            plan = self._tc_verified(ds, omega, n, plan, tag)
         if plan is not None:
             self._gram_tc(plan, omega, J)
             plan.uses += 1
@@ -431,12 +455,12 @@ class GibbsEngine(object):
         self.h2d_bytes += Wt.nbytes
         return self.K.to_device(Wt)
 
-    def build_Wt_device(self, state, lo, hi):
+    def build_Wt_device(self, state, lo, hi, tag=None):
         """The same from the device copy of the new state (rows [a (N) | W (N*B) | b | status] per neuron), so the
         next sweep's psi / PG / Gram can be enqueued without a host round trip."""
         n = hi - lo
         N, NB = self.N, self.N * self.B
-        Wt = self._wsbuf("Wt", (self.ldx, pad_ldn(n)), zero=True)
+        Wt = self._wsbuf("Wt" if tag is None else "Wt@%s" % (tag,), (self.ldx, pad_ldn(n)), zero=True)
         rows = state[lo:hi]
         Wt[:NB, :n] = (rows[:, :N].unsqueeze(-1) * rows[:, N:N + NB].reshape(n, N, self.B)).reshape(n, NB).t()
         Wt[NB, :n] = rows[:, N + NB]
@@ -464,17 +488,22 @@ class GibbsEngine(object):
             raise ValueError("at most %d data sets per model: the Philox call ids of a sweep are laid out in strides "
                              "of %d (PG draws of data set i, then the scan)" % (self.CALL_STRIDE - 2, self.CALL_STRIDE))
 
-    def _augment(self, datasets, Wt, call_base):
+    def _augment(self, datasets, Wt, call_base, blk=None):
         """psi -> omega ~ PG(1, psi) -> J for the scan block, for every dataset (regression.py:496-508, :225-262).
-        Everything is enqueued on the current stream; nothing here waits for the device."""
+        Everything is enqueued on the current stream; nothing here waits for the device.
+        blk = (lo, hi, tag): the same for one neuron group of the overlapped single-GPU sweep, with the group's own
+        buffers (the PG draws are keyed by the global (bin, neuron) index, so grouping does not change them)."""
         K, N, D, ldx = self.K, self.N, self.D, self.ldx
-        p_lo, p_hi = self.psi_lo, self.psi_hi
-        nP, nS = p_hi - p_lo, self.scan_hi - self.scan_lo
+        p_lo, p_hi = (self.psi_lo, self.psi_hi) if blk is None else blk[:2]
+        tag = None if blk is None else blk[2]
+        sfx = "" if tag is None else "@%s" % (tag,)
+        nP = p_hi - p_lo
+        nS = self.scan_hi - self.scan_lo if blk is None else nP
         ldn = Wt.shape[1]
-        J = self._wsbuf("J", (max(nS, 1) if self._time_sharded() else nP, ldx, ldx), zero=True)
+        J = self._wsbuf("J" + sfx, (max(nS, 1) if self._time_sharded() else nP, ldx, ldx), zero=True)
         for di, ds in enumerate(datasets):
-            psi = self._buf(ds, "psi", (ds.T, ldn))
-            omega = self._buf(ds, "omega", (ds.T, ldn), zero=True)
+            psi = self._buf(ds, "psi" + sfx, (ds.T, ldn))
+            omega = self._buf(ds, "omega" + sfx, (ds.T, ldn), zero=True)
             e0 = self._mark("activation")
             K.activation(ds.Xp, Wt, D, nP, out=psi)
             e1 = self._mark("activation", e0)
@@ -485,10 +514,10 @@ class GibbsEngine(object):
                 omega[:, :nP] = K.to_device(om)
             e2 = self._mark("pg_draw", e1)
             if di == 0:
-                self.weighted_gram(ds, omega, nP, J)
+                self.weighted_gram(ds, omega, nP, J, tag)
             else:
-                Jd = self._wsbuf("J_extra", tuple(J.shape), zero=True)
-                self.weighted_gram(ds, omega, nP, Jd)
+                Jd = self._wsbuf("J_extra" + sfx, tuple(J.shape), zero=True)
+                self.weighted_gram(ds, omega, nP, Jd, tag)
                 J += Jd
             self._mark("weighted_gram", e2)
         self._aug_end = self._mark("idle_before_scan")        # start of the gap until the scan kernel is enqueued
@@ -500,6 +529,8 @@ class GibbsEngine(object):
         pend, self._pending = self._pending, None
         if pend is None or self.inject is not None:
             return None
+        if len(pend) != 5:
+            return None                                      # left by the overlapped sweep (per-group Grams)
         ds_ids, A0, W0, b0, J = pend
         if ds_ids != [id(ds) for ds in datasets]:
             return None
@@ -541,6 +572,159 @@ class GibbsEngine(object):
         self.h2d_bytes += stage.numel() * 8 + nb
         return out, bdev[:a_host.size].view(a_host.shape), bdev[a_host.size:]
 
+    # ------------------------------------------------------------------ overlapped single-GPU sweep
+    OVERLAP_MIN_N = 128
+
+    def _overlap_groups(self, datasets):
+        """Neuron groups of the overlapped sweep, or None when the sweep runs as one block (multi-GPU runs, small
+        models, injected randomness, no data, on-device rate moments -- they read the psi buffer of the whole block)."""
+        if not (self.overlap and self.pipeline and self.inject is None and datasets and self.comm.world == 1
+                and self.K.device.type == "cuda" and self.N >= max(2, self.overlap_min_n)):
+            return None
+        if self.moments is not None and self.moments.rates:
+            return None
+        h = (self.N + 1) // 2
+        return [(0, h, 0), (h, self.N, 1)]
+
+    def _overlap_streams(self):
+        if self._ovl is None:
+            dev = self.K.device
+            # the scan stream has the higher priority: when the Gram of a group retires, the scan CTAs of that group
+            # take their SMs before the next group's psi / PG / Gram kernels fill the machine
+            self._ovl = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1))
+        return self._ovl
+
+    def _overlap_drain(self):
+        """Order the current stream behind whatever the two side streams still hold (mode switches, scoring calls)."""
+        if self._ovl is not None:
+            cur = torch.cuda.current_stream(self.K.device)
+            for st in self._ovl:
+                cur.wait_stream(st)
+
+    def _sweep_overlapped(self, groups, datasets, A, W, b, hypers, call_base):
+        """The single-GPU sweep as TWO neuron groups on two streams.  Regressions are independent given the
+        hyper-parameters (models.py:169-171 is a loop over them), so the groups only meet in the host network step:
+
+            stream `aug` :  psi/PG/Gram_k(g1)   | psi/PG/Gram_k+1(g0) | psi/PG/Gram_k+1(g1) | psi/PG/Gram_k+2(g0) | ...
+            stream `scan`:  scan_k(g0)          | scan_k(g1)          | scan_k+1(g0)        | scan_k+1(g1)        | ...
+                            `------------- sweep k ------------'      `------------ sweep k+1 ------------'
+
+        One group's scan is a single wave of <= 148 one-CTA neurons, latency bound (~2.5 ms at cfg3) and leaves the
+        other SMs idle; here those SMs -- and all of them once the scan CTAs retire -- work on the other group's
+        augmentation.  Measured at cfg3 (profiles/r02z_timeline_aug_first.log): psi + PG of the other group finish
+        inside the scan's 2.5 ms and the Gram follows at full width -- 2 x 8.0 ms per sweep while the chain is sparse,
+        but no gain at its equilibrium density, where the scan is L2-bound (see the note at `self.overlap`).  Should a
+        Gram start while scan CTAs still hold SMs, it draws its items from a device counter (gram_tc.cu,
+        tc_work_ticket), so CTAs that start late just take fewer items.
+        Call k submits aug_k(g1) first -- it needs nothing from the host, and keeps the device busy while the host
+        prepares the prior terms (2 ms of numpy at cfg3) -- then scan_k(g0), scan_k(g1) and the NEXT sweep's aug(g0),
+        which is on the device while the caller runs its network step.  A host that is late with scan_k(g0) loses the
+        overlap (the persistent Gram CTAs of g1 are not preempted), nothing else.  The chain is the one the one-block
+        sweep produces: PG draws and scan randomness are keyed by global (bin, neuron) / neuron indices, the Gram sums
+        are exact integers, and every other kernel works neuron by neuron."""
+        K, N, B, D, ldx = self.K, self.N, self.B, self.D, self.ldx
+        NB = N * B
+        (lo0, hi0, tag0), (lo1, hi1, tag1) = groups
+        s_aug, s_scan = self._overlap_streams()
+        main = torch.cuda.current_stream(K.device)
+        pend, self._pending = self._pending, None
+        aug0 = prev_state = None
+        if pend is not None and len(pend) == 6 and pend[5] == "groups":
+            ds_ids, A0, W0, b0, (aug0, prev_state), _ = pend
+            if ds_ids != [id(ds) for ds in datasets] or not (np.array_equal(A0, A) and np.array_equal(W0, W)
+                                                              and np.array_equal(b0, b)):
+                aug0 = prev_state = None                     # the user edited the state or swapped data: start over
+        s_aug.wait_stream(main)
+        s_scan.wait_stream(main)
+        for ds in datasets:
+            if "side_streams" not in ds.buffers:
+                # allocated on the caller's stream, used on the side streams: a later free must wait for them
+                for t in (ds.Xp, ds.Y):
+                    t.record_stream(s_aug)
+                    t.record_stream(s_scan)
+                ds.buffers["side_streams"] = True
+
+        def augment(lo, hi, tag, src_state, base):
+            """psi / PG / Gram of one group on the aug stream, from device state rows (or the host state)."""
+            with torch.cuda.stream(s_aug):
+                Wt = self.build_Wt(A, W, b, lo, hi) if src_state is None else \
+                    self.build_Wt_device(src_state, lo, hi, tag=tag)
+                J = self._augment(datasets, Wt, base, blk=(lo, hi, tag))
+                ev = torch.cuda.Event()
+                ev.record()
+            return J, ev
+
+        if aug0 is None:
+            aug0 = augment(lo0, hi0, tag0, None, call_base)
+        # group 1's augmentation of THIS sweep: from the rows the previous sweep left on the device
+        aug1 = augment(lo1, hi1, tag1, prev_state, call_base)
+        width = self._state_width()
+        with torch.cuda.stream(s_scan):
+            state = self._wsbuf("state@%d" % (self.calls & 1), (N, width), zero=True)
+            h_S = self._h_for_scan(datasets)
+            pr = prior_arrays(hypers["rho"], hypers["mu_w"], hypers["S_w"], hypers["mu_b"], hypers["S_b"])
+            do_scan = pr.pop("do_scan")
+            a_host = np.array(A, dtype=np.uint8)
+            det = ~do_scan
+            a_host[det] = np.round(hypers["rho"][det]).astype(np.uint8)      # regression.py:274-275
+            prior, a_dev, do_scan_dev = self._upload_priors(pr, a_host, do_scan)
+            perm, us, z = K.scan_randomness(N, B, N, 0, self.seed, call_base + self.CALL_STRIDE - 1)
+
+        def scan(lo, hi, tag, J_g, ev_aug):
+            n = hi - lo
+            with torch.cuda.stream(s_scan):
+                s_scan.wait_event(ev_aug)
+                P_ws = self._wsbuf("P@%s" % (tag,), (n * D * D,))
+                e3 = self._mark("spike_slab")
+                W_new, b_new, _, _, status = K.spike_slab_update(
+                    N, B, J_g, h_S[lo:hi], {k: v[lo:hi] for k, v in prior.items()}, perm[lo:hi], us[lo:hi], z[lo:hi],
+                    do_scan_dev[lo:hi], a_dev[lo:hi], P_ws=P_ws)
+                self._mark("spike_slab", e3)
+                state[lo:hi, :N] = a_dev[lo:hi]
+                state[lo:hi, N:N + NB] = W_new.reshape(n, NB)
+                state[lo:hi, N + NB] = b_new
+                state[lo:hi, N + NB + 1] = status
+                ev = torch.cuda.Event()
+                ev.record()
+            return ev
+
+        ev_scan0 = scan(lo0, hi0, tag0, *aug0)
+        scan(lo1, hi1, tag1, *aug1)
+        with torch.cuda.stream(s_scan):
+            stage = self._pinned("state", (N, width), torch.float64)
+            stage.copy_(state, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            if self.moments is not None:
+                self.moments.add_state(state, N + NB + 1)
+        # group 0's augmentation of the NEXT sweep, behind its scan: on the device while the host does its part
+        s_aug.wait_event(ev_scan0)
+        nxt0 = augment(lo0, hi0, tag0, state, call_base + self.CALL_STRIDE)
+        main.wait_event(done)            # the caller's stream (and its timing events) sees the sweep's result
+        done.synchronize()
+        return self._finish_sweep(stage, datasets, (nxt0, state), groups=True)
+
+    def _finish_sweep(self, stage, datasets, pend_J, groups=False):
+        """Host side of the end of a sweep: unpack the pinned state rows, surface failed neurons, remember what the
+        pre-launched augmentation was computed from."""
+        N, NB, B = self.N, self.N * self.B, self.B
+        host = stage.numpy()
+        self.d2h_bytes += host.nbytes
+        A_out = host[:, :N] != 0
+        W_out = host[:, N:N + NB].reshape(-1, N, B).copy()
+        b_out = host[:, N + NB].copy()
+        st = host[:, N + NB + 1]
+        if st.any():
+            self._pending = None
+            bad = np.nonzero(st)[0]
+            raise FloatingPointError("spike-and-slab update lost positive definiteness for neuron(s) %s "
+                                     "(ill-conditioned posterior precision)" % bad[:8].tolist())
+        if pend_J is not None:
+            # private copies: the caller's regressions alias the returned arrays and may edit them in place
+            self._pending = ([id(ds) for ds in datasets], A_out.copy(), W_out.copy(), b_out.copy(), pend_J) \
+                + (("groups",) if groups else ())
+        return A_out, W_out, b_out
+
     def sweep(self, datasets, A, W, b, hypers):
         """One resample_regressions() (models.py:169-171) for all neurons.
         A (N,N) bool, W (N,N,B), b (N,) host state;  hypers: dict rho (N,N), mu_w (N,N,B), S_w (N,N,B,B),
@@ -559,6 +743,10 @@ class GibbsEngine(object):
         call_base = self.calls * self.CALL_STRIDE
         self._check_call_ids(datasets)
         self._tc_poll()
+        groups = self._overlap_groups(datasets)
+        if groups is not None:
+            return self._sweep_overlapped(groups, datasets, A, W, b, hypers, call_base)
+        self._overlap_drain()
 
         J_S = h_S = None
         if datasets:
@@ -632,21 +820,7 @@ class GibbsEngine(object):
                 mom.add_rates(di, psi, nP)
         if done is not None:
             done.synchronize()
-        host = stage.numpy()
-        self.d2h_bytes += host.nbytes
-        A_out = host[:, :N] != 0
-        W_out = host[:, N:N + NB].reshape(-1, N, B).copy()
-        b_out = host[:, N + NB].copy()
-        st = host[:, N + NB + 1]
-        if st.any():
-            self._pending = None
-            bad = np.nonzero(st)[0]
-            raise FloatingPointError("spike-and-slab update lost positive definiteness for neuron(s) %s "
-                                     "(ill-conditioned posterior precision)" % bad[:8].tolist())
-        if pend_J is not None:
-            # private copies: the caller's regressions alias the returned arrays and may edit them in place
-            self._pending = ([id(ds) for ds in datasets], A_out.copy(), W_out.copy(), b_out.copy(), pend_J)
-        return A_out, W_out, b_out
+        return self._finish_sweep(stage, datasets, pend_J)
 
     # ------------------------------------------------------------------ Gaussian observations
     def _gaussian_stats(self, datasets):

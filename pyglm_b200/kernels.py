@@ -197,13 +197,15 @@ class CudaKernels(object):
         self._call("pyglm_column_max", self._p(A), ld, T, ncols, self._p(cmax), self._p(neg), self._stream())
         return cmax, bool(neg.item())
 
-    def gram_tc_plan(self, Xp, D, n_valid, S=4, comm=None, t_off=0, stream=False):
+    def gram_tc_plan(self, Xp, D, n_valid, S=4, comm=None, t_off=0, stream=False, share=None):
         """Sweep-invariant operand of the tensor-core Gram (once per dataset) and its per-sweep buffers.
         stream=False: the digit planes of Z = X~_i X~_j stay resident in HBM (S * pairs * T bytes); stream=True: only
         the fixed-point design (4 * D * T bytes) is kept and the kernel builds the Z tiles in shared memory (S = 4).
         Both give the same integer sums.  Raises ValueError when the design has negative entries.  comm / t_off:
-        time-sharded runs (Xp is the slab starting at global bin t_off; scales are all-reduced over `comm`)."""
-        return TcGramPlan(self, Xp, D, n_valid, S, comm=comm, t_off=t_off, stream=stream)
+        time-sharded runs (Xp is the slab starting at global bin t_off; scales are all-reduced over `comm`).
+        share: another plan of the SAME design (same Xp, S, mode) whose sweep-invariant operand is reused -- plans of
+        different neuron groups of one data set then differ only in their per-sweep buffers (Os, omax, Jint)."""
+        return TcGramPlan(self, Xp, D, n_valid, S, comm=comm, t_off=t_off, stream=stream, share=share)
 
     def gram_tc_stream_tiles(self, D):
         key = ("tc_stream_tiles", D)
@@ -282,7 +284,7 @@ class TcGramPlan(object):
     and of omega) are all-reduced (max) over the ranks and the rounding dither is keyed by the global time bin, so
     the integer partial sums of the slabs add up -- exactly, in int64 -- to the Jint a single GPU would compute."""
 
-    def __init__(self, K, Xp, D, n_valid, S=4, comm=None, t_off=0, stream=False):
+    def __init__(self, K, Xp, D, n_valid, S=4, comm=None, t_off=0, stream=False, share=None):
         self.K, self.D, self.n, self.S = K, D, n_valid, S
         self.stream = bool(stream)
         if self.stream and S != 4:
@@ -294,8 +296,17 @@ class TcGramPlan(object):
         self.T, self.ldx = Xp.shape
         g = K.gram_tc_geometry(D, n_valid, self.T, S)
         self.geom = g
-        self.cmax = K.empty(D)
         self.neg = K.empty(1, dtype=torch.int32)
+        if share is not None:
+            assert (share.D, share.S, share.T, share.ldx, share.stream) == (D, S, self.T, self.ldx, self.stream)
+            self.cmax, self.Zs, self.tiles = share.cmax, share.Zs, getattr(share, "tiles", None)
+            self.xq, self.rw = getattr(share, "xq", None), getattr(share, "rw", None)
+            self.neg.zero_()
+            self.Os = torch.zeros(S, g["Npad"], g["Tpad"], dtype=torch.uint8, device=K.device)
+            self.omax = K.empty(n_valid)
+            self.Jint = K.empty(n_valid, g["Mpad"], dtype=torch.int64)
+            return
+        self.cmax = K.empty(D)
         K._call("pyglm_column_max", K._p(Xp), self.ldx, self.T, D, K._p(self.cmax), K._p(self.neg), K._stream())
         if self.comm is not None:
             self.comm.all_reduce_max(self.cmax)

@@ -284,6 +284,7 @@ class NonlinearAutoregressiveModel(object):
         """dict(n, A_mean (N,N), W_mean / W_var (N,N,B), b_mean / b_var (N,), rate_mean / rate_var: per data set the
         (T_local, n_local) block this rank computes -- all of it on a single GPU -- or None)."""
         mom = self.engine.moments
+        self.engine._overlap_drain()         # the sums may have been updated on the overlapped sweep's side streams
         assert mom is not None and mom.n > 0, "call start_collecting() and run at least one sweep first"
         N, B, n = self.N, self.B, float(mom.n)
         m1 = (mom.s1 / n).cpu().numpy()

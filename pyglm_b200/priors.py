@@ -21,21 +21,38 @@ def prior_arrays(rho, mu_w, S_w, mu_b, S_b):
     S_b = np.asarray(S_b, dtype=np.float64).reshape(-1)
     B = S_w.shape[-1]
     if B <= 2:
-        # closed forms: numpy's batched inv / slogdet pay a LAPACK call per B x B block (40000 of them at cfg3)
+        # closed forms on contiguous component planes: numpy's batched inv / slogdet pay a LAPACK call per B x B block
+        # (40000 of them at cfg3), and arithmetic on the strided views S_w[..., i, j] is several times slower than on
+        # planes -- this runs on the host between two sweeps, on the critical path of the overlapped sweep
+        shp = S_w.shape[:-2]
         if B == 1:
-            det = S_w[..., 0, 0]
+            det = S_w.reshape(shp)
             J0w = 1.0 / S_w
+            pos = det > 0
+            h0w = J0w.reshape(shp + (1,)) * mu_w
+            quad = (mu_w * h0w).reshape(shp)
         else:
-            s00, s01, s10, s11 = S_w[..., 0, 0], S_w[..., 0, 1], S_w[..., 1, 0], S_w[..., 1, 1]
-            det = s00 * s11 - s01 * s10
-            J0w = np.empty_like(S_w)
-            J0w[..., 0, 0], J0w[..., 0, 1], J0w[..., 1, 0], J0w[..., 1, 1] = s11 / det, -s01 / det, -s10 / det, s00 / det
-        if np.any(~(det > 0)) or np.any(~(S_w[..., 0, 0] > 0)):
+            Sp = np.ascontiguousarray(S_w.reshape(-1, 4).T)              # planes s00, s01, s10, s11
+            mp = np.ascontiguousarray(mu_w.reshape(-1, 2).T)             # planes mu0, mu1
+            det = Sp[0] * Sp[3] - Sp[1] * Sp[2]
+            pos = (det > 0) & (Sp[0] > 0)
+            inv = 1.0 / det
+            Jp = np.empty_like(Sp)
+            np.multiply(Sp[3], inv, out=Jp[0])
+            np.multiply(Sp[1], -inv, out=Jp[1])
+            np.multiply(Sp[2], -inv, out=Jp[2])
+            np.multiply(Sp[0], inv, out=Jp[3])
+            hp = np.empty_like(mp)
+            hp[0] = Jp[0] * mp[0] + Jp[1] * mp[1]
+            hp[1] = Jp[2] * mp[0] + Jp[3] * mp[1]
+            J0w = np.ascontiguousarray(Jp.T).reshape(S_w.shape)
+            h0w = np.ascontiguousarray(hp.T).reshape(mu_w.shape)
+            # h0w^T S_w h0w = mu_w^T J0w mu_w = mu_w . h0w
+            quad = (mp[0] * hp[0] + mp[1] * hp[1]).reshape(shp)
+            det = det.reshape(shp)
+        if not np.all(pos):
             raise ValueError("S_w must be positive definite")
         logdet = -np.log(det)
-        h0w = (J0w * mu_w[..., None, :]).sum(-1)
-        # h0w^T S_w h0w = mu_w^T J0w mu_w = mu_w . h0w
-        quad = (mu_w * h0w).sum(-1)
     else:
         J0w = np.linalg.inv(S_w)
         h0w = np.einsum("nmbc,nmc->nmb", J0w, mu_w)

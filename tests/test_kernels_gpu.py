@@ -610,3 +610,50 @@ def test_scan_randomness_is_a_permutation_and_shard_invariant(K):
     u = us.cpu().numpy()
     assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.1
     assert abs(float(z.mean())) < 0.2 and abs(float(z.std()) - 1) < 0.2
+
+
+# ----------------------------------------------------------------------------- peer-memory exchange kernels
+def test_peer_kernels_on_one_device(K):
+    """The two exchange kernels of the multi-GPU sweep (csrc/peer.cu, gram_tc_finalize_peers_kernel) driven with
+    pointer tables that all live on this device -- `world` buffers standing in for the ranks' peer-mapped memory:
+    pyglm_gram_tc_finalize_peers must equal pyglm_gram_tc_finalize of the exact int64 sum of the partial Jint buffers
+    (the fused reduce-scatter), and pyglm_peer_push must land the rows at the same offset of every buffer."""
+    T, N, B, n_loc, world = 3000, 6, 3, 20, 3
+    Xp, X, om = _tc_inputs(K, T, N, B, n_loc, seed=5)
+    D = N * B + 1
+    plan = K.gram_tc_plan(Xp, D, n_loc, 4)
+    plan.slice_omega(K.to_device(om))
+    Jint = plan.mma().clone()
+    g = plan.geom
+    # split the exact integer sums into `world` partial buffers of (n_max * world) rows, like the time slabs' partials
+    rng = np.random.default_rng(0)
+    n_max = (n_loc + world - 1) // world
+    rows = n_max * world
+    parts = []
+    rest = torch.zeros(rows, g["Mpad"], dtype=torch.int64, device=K.device)
+    rest[:n_loc] = Jint
+    for r in range(world - 1):
+        p = torch.from_numpy(rng.integers(-2 ** 40, 2 ** 40, size=(rows, g["Mpad"]))).to(K.device)
+        parts.append(p)
+        rest = rest - p
+    parts.append(rest)
+    table = torch.tensor([p.data_ptr() for p in parts], dtype=torch.int64, device=K.device)
+    J_ref = plan.finalize(K.zeros(n_loc, plan.ldx, plan.ldx))
+
+    class _Hdl(object):
+        buffer_ptrs_dev = table.data_ptr()
+
+    for rank in range(world):
+        lo, hi = rank * n_max, min(n_loc, (rank + 1) * n_max)
+        if hi <= lo:
+            continue
+        J = plan.finalize_peers(K.zeros(hi - lo, plan.ldx, plan.ldx), _Hdl, world, lo, hi - lo,
+                                plan.omax[lo:hi].contiguous())
+        assert torch.equal(J, J_ref[lo:hi])
+    # push: rows of "rank 1" into every buffer at its offset
+    bufs = [torch.zeros(world * 4, 10, dtype=torch.float64, device=K.device) for _ in range(world)]
+    tab2 = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=K.device)
+    src = K.to_device(rng.standard_normal((4, 10)))
+    K._call("pyglm_peer_push", K._p(src), src.numel() * 8, tab2.data_ptr(), world, 1 * 4 * 10 * 8, K._stream())
+    for b in bufs:
+        assert torch.equal(b[4:8], src) and float(b[:4].abs().sum()) == 0.0 and float(b[8:].abs().sum()) == 0.0

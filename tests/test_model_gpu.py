@@ -295,16 +295,20 @@ def test_generate_rate_statistics():
     assert m.generate(T=0) .shape == (0, N)
 
 
-def _chain_states(pipeline, edit_at=None, n_sweeps=5):
+def _chain_states(pipeline, edit_at=None, n_sweeps=5, overlap=False, gram="auto", collect=False):
     from pyglm_b200.models import SparseBernoulliGLM
     from pyglm_b200.utils.basis import cosine_basis
     N, B, L, T = 9, 2, 20, 4000
     basis = cosine_basis(B, L=L) / L
     Y = (np.random.default_rng(5).random((T, N)) < 0.08).astype(np.float64)
     np.random.seed(0)
-    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=21)
+    m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=21, gram=gram)
     m.add_data(Y)
     m.engine.pipeline = pipeline
+    m.engine.overlap = overlap
+    m.engine.overlap_min_n = 0
+    if collect:
+        m.start_collecting()
     out = []
     for k in range(n_sweeps):
         if k == edit_at:                      # the user edits the state between sweeps (examples/synthetic.py:30-32)
@@ -313,6 +317,8 @@ def _chain_states(pipeline, edit_at=None, n_sweeps=5):
             m.regressions[4].b[:] = -1.0
         m.resample_model()
         out.append((m.adjacency.copy(), m.weights.copy(), m.biases.copy()))
+    if collect:
+        out.append(m.posterior_moments())
     return out
 
 
@@ -324,6 +330,46 @@ def test_pipelined_sweeps_equal_unpipelined(edit_at):
     a = _chain_states(True, edit_at)
     b = _chain_states(False, edit_at)
     for (A1, W1, b1), (A2, W2, b2) in zip(a, b):
+        assert np.array_equal(A1, A2) and np.array_equal(W1, W2) and np.array_equal(b1, b2)
+
+
+@pytest.mark.parametrize("gram", ["fp64", "tc"])
+@pytest.mark.parametrize("edit_at", [None, 2])
+def test_overlapped_sweeps_equal_one_block_sweeps(edit_at, gram):
+    """Single-GPU sweeps of large models run as two neuron groups on two streams (engine._sweep_overlapped: the scan of
+    one group shares the GPU with the psi / PG / Gram of the other; the tensor-core Gram draws its items from a device
+    counter).  Regressions are independent given the hyper-parameters (models.py:169-171) and all randomness is keyed
+    by global indices, so the chain must equal the one-block chain bit for bit -- also when the user edits the state
+    between sweeps, and with the on-device moments collected on the side streams."""
+    a = _chain_states(True, edit_at, overlap=True, gram=gram, collect=True)
+    b = _chain_states(True, edit_at, overlap=False, gram=gram, collect=True)
+    for (A1, W1, b1), (A2, W2, b2) in zip(a[:-1], b[:-1]):
+        assert np.array_equal(A1, A2) and np.array_equal(W1, W2) and np.array_equal(b1, b2)
+    for k in ("A_mean", "W_mean", "W_var", "b_mean"):
+        assert np.array_equal(a[-1][k], b[-1][k])
+
+
+def test_overlapped_sweeps_switch_modes_mid_chain():
+    """Turning the overlap off and on between sweeps (bench.py does it for the per-kernel timing pass) discards the
+    pre-launched augmentation of the other mode and leaves the chain unchanged."""
+    from pyglm_b200.models import SparseBernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+    N, B, L, T = 9, 2, 20, 4000
+    basis = cosine_basis(B, L=L) / L
+    Y = (np.random.default_rng(5).random((T, N)) < 0.08).astype(np.float64)
+    chains = []
+    for pattern in ([True, False, False, True, True, False], [False] * 6):
+        np.random.seed(0)
+        m = SparseBernoulliGLM(N, basis=basis, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=21)
+        m.add_data(Y)
+        m.engine.overlap_min_n = 0
+        out = []
+        for on in pattern:
+            m.engine.overlap = on
+            m.resample_model()
+            out.append((m.adjacency.copy(), m.weights.copy(), m.biases.copy()))
+        chains.append(out)
+    for (A1, W1, b1), (A2, W2, b2) in zip(*chains):
         assert np.array_equal(A1, A2) and np.array_equal(W1, W2) and np.array_equal(b1, b2)
 
 
