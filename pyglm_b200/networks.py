@@ -86,6 +86,14 @@ class _NetworkModel(object):
     def rvs(self, size=[]):
         return None
 
+    # Hooks through which a structured WEIGHT prior takes part in the moves of the latent variables it shares with a
+    # structured ADJACENCY prior (block labels z, locations L): the extra log-likelihood of the weights, 0 here.
+    def _weight_block_scores(self, n):
+        return 0.0
+
+    def _weight_location_score(self, n, l):
+        return 0.0
+
     # state exchanged between ranks in multi-GPU runs (rank 0 resamples, the others receive)
     def get_state(self):
         return {}
@@ -349,7 +357,7 @@ class _StochasticBlockAdjacencyMixin(_NetworkModel):
         A, W = data
         N, C = self.N, self.C
         for n in np.random.permutation(N):
-            s = self.block_scores(A, n)
+            s = self.block_scores(A, n) + self._weight_block_scores(n)
             pr = np.exp(s - s.max())
             self.z[n] = np.searchsorted(np.cumsum(pr), np.random.rand() * pr.sum())
         Z = np.eye(C)[self.z]
@@ -418,7 +426,9 @@ class _LatentDistanceAdjacencyMixin(_NetworkModel):
         N = self.N
         links = A.astype(np.float64) + A.T                  # links[n, m]: how many of n<-m, m<-n are present
         for n in np.random.permutation(N):
-            self.L[n], _ = elliptical_slice(self.L[n], lambda l, n=n: self.location_score(links, n, l), self.sigma_l)
+            self.L[n], _ = elliptical_slice(
+                self.L[n], lambda l, n=n: self.location_score(links, n, l) + self._weight_location_score(n, l),
+                self.sigma_l)
         off = _offdiag(N)
         negd = (self.logits() - self.gamma)[off]
         a_off = A[off].astype(np.float64)
@@ -440,6 +450,217 @@ class _LatentDistanceAdjacencyMixin(_NetworkModel):
         s = state["distance"]
         self.L, self.gamma = np.array(s["L"]), float(s["gamma"])
         self._self_betabernoulli.rho = s["rho_self"]
+
+
+def _gauss_logpdf(x, mu, sigma):
+    """log N(x; mu, sigma) for stacks: x, mu (..., B), sigma (..., B, B) -> (...)."""
+    d = x - mu
+    sol = np.linalg.solve(sigma, d[..., None])[..., 0]
+    _, logdet = np.linalg.slogdet(sigma)
+    return -0.5 * ((d * sol).sum(-1) + logdet + x.shape[-1] * np.log(2.0 * np.pi))
+
+
+class _StochasticBlockWeightsMixin(_NetworkModel):
+    """Block-dependent weights (the weight half of the "stochastic block models" TODO at networks.py:175; the SBM row
+    of Linderman, Adams & Pillow 2016, README.md:26-28): W[n, n'] | a = 1 ~ N(mu[z_n, z_n'], Sigma[z_n, z_n']) for the
+    connection n' -> n, every block pair with its own NIW-conjugate Gaussian (NIWGaussian, as the shared prior of
+    networks.py:76-149), self-connections with theirs.  Put FIRST among the bases: combined with
+    _StochasticBlockAdjacencyMixin the two share the labels z, and z_n is then resampled from the adjacency AND the
+    weights of row / column n (the hook _weight_block_scores); over any other adjacency prior the mixin keeps its own
+    labels, z_n ~ Cat(pi), pi ~ Dir(alpha).  Host step, O(N^2 C B^2) per sweep.  Not in the reference snapshot:
+    parity unpinned, validated against brute-force conditionals and by recovery of planted structure."""
+
+    def __init__(self, N, B, C=2, alpha=1.0, z=None, mu_0=0.0, sigma_0=1.0, kappa_0=1.0, nu_0=3.0, **kwargs):
+        super(_StochasticBlockWeightsMixin, self).__init__(N, B, C=C, alpha=alpha, z=z, **kwargs)
+        self._shares_z = isinstance(self, _StochasticBlockAdjacencyMixin)
+        if not self._shares_z:
+            self.C = int(C)
+            self.alpha = np.array(expand_scalar(alpha, (self.C,)), dtype=np.float64)
+            self.pi = np.random.dirichlet(self.alpha)
+            self.z = np.random.choice(self.C, size=N, p=self.pi) if z is None else np.array(z, dtype=np.int64)
+            assert self.z.shape == (N,) and self.z.min() >= 0 and self.z.max() < self.C
+        mu_0 = expand_scalar(mu_0, (B,))
+        sigma_0 = expand_cov(sigma_0, (B, B))
+        nu = max(nu_0, B + 2.)
+        self._block_gaussians = [[NIWGaussian(mu_0, sigma_0, kappa_0, nu) for _ in range(self.C)]
+                                 for _ in range(self.C)]
+        self._self_gaussian = NIWGaussian(mu_0, sigma_0, kappa_0, nu_0)
+        self._AW = None
+
+    @property
+    def block_mu(self):
+        return np.array([[g.mu for g in row] for row in self._block_gaussians])            # (C, C, B)
+
+    @property
+    def block_sigma(self):
+        return np.array([[g.sigma for g in row] for row in self._block_gaussians])         # (C, C, B, B)
+
+    @property
+    def mu_W(self):
+        mu = self.block_mu[np.ix_(self.z, self.z)]
+        mu[np.diag_indices(self.N)] = self._self_gaussian.mu
+        return mu
+
+    @property
+    def sigma_W(self):
+        sigma = self.block_sigma[np.ix_(self.z, self.z)]
+        sigma[np.diag_indices(self.N)] = self._self_gaussian.sigma
+        return sigma
+
+    def _weight_block_scores(self, n):
+        """log p(present weights of row and column n | z_n = c, the rest) for every c."""
+        A, W = self._AW
+        mu, sigma = self.block_mu, self.block_sigma
+        out = np.zeros(self.C)
+        row = np.flatnonzero(A[n])
+        row = row[row != n]
+        col = np.flatnonzero(A[:, n])
+        col = col[col != n]
+        for c in range(self.C):
+            if row.size:
+                out[c] += _gauss_logpdf(W[n, row], mu[c, self.z[row]], sigma[c, self.z[row]]).sum()
+            if col.size:
+                out[c] += _gauss_logpdf(W[col, n], mu[self.z[col], c], sigma[self.z[col], c]).sum()
+        return out
+
+    def resample(self, data=[]):
+        A, W = data
+        self._AW = (A, W)                     # the shared-label move of the adjacency mixin reads it through the hook
+        # block parameters given the labels, then the labels (own, or -- further down the chain -- the shared ones)
+        off = A & _offdiag(self.N)
+        for c in range(self.C):
+            for c2 in range(self.C):
+                m = off & (self.z[:, None] == c) & (self.z[None, :] == c2)
+                self._block_gaussians[c][c2].resample(W[m])
+        self._self_gaussian.resample(W[np.arange(self.N), np.arange(self.N)][A.diagonal()])
+        if not self._shares_z:
+            for n in np.random.permutation(self.N):
+                s = np.log(self.pi) + self._weight_block_scores(n)
+                pr = np.exp(s - s.max())
+                self.z[n] = np.searchsorted(np.cumsum(pr), np.random.rand() * pr.sum())
+            counts = np.bincount(self.z, minlength=self.C)
+            self.pi = np.maximum(np.random.dirichlet(self.alpha + counts), 1e-300)
+        super(_StochasticBlockWeightsMixin, self).resample(data)
+
+    def get_state(self):
+        s = super(_StochasticBlockWeightsMixin, self).get_state()
+        s["block_weights"] = dict(mu=self.block_mu, sigma=self.block_sigma, self_gaussian=self._self_gaussian.get_params(),
+                                  z=self.z.copy(), pi=np.array(self.pi))
+        return s
+
+    def set_state(self, state):
+        super(_StochasticBlockWeightsMixin, self).set_state(state)
+        s = state["block_weights"]
+        for c in range(self.C):
+            for c2 in range(self.C):
+                self._block_gaussians[c][c2].set_params(s["mu"][c, c2], s["sigma"][c, c2])
+        self._self_gaussian.set_params(**s["self_gaussian"])
+        if not self._shares_z:
+            self.z, self.pi = np.array(s["z"]), np.array(s["pi"])
+
+
+class _LatentDistanceWeightsMixin(_NetworkModel):
+    """Distance-dependent weights (the weight half of the "distance models" TODO at networks.py:261; the latent
+    distance row of Linderman, Adams & Pillow 2016, whose mean weight falls off as -|l_n - l_n'|^2 + mu_0):
+    W[n, n'] | a = 1 ~ N(m + beta |l_n - l_n'|^2, Sigma), with the B x 2 coefficient matrix Theta = [m, beta] and Sigma
+    under the conjugate matrix-normal inverse-Wishart prior Theta | Sigma ~ MN(M_0, Sigma, V_0), Sigma ~ IW(S_0, nu_0)
+    (M_0 = [mu_0, beta_0], beta_0 = -1 by default: closer neurons, stronger weights).  Self-connections keep their own
+    NIW Gaussian.  Put FIRST among the bases: combined with _LatentDistanceAdjacencyMixin the two share the locations
+    L, and each elliptical-slice move of l_n then sees the adjacency AND the weights of row / column n (the hook
+    _weight_location_score); over any other adjacency prior the mixin keeps its own locations, l_n ~ N(0, sigma_l^2 I).
+    Host step, O(N^2 (dim + B^2)) per sweep.  Not in the reference snapshot: parity unpinned."""
+
+    def __init__(self, N, B, dim=2, sigma_l=1.0, L=None, mu_0=0.0, beta_0=-1.0, v_0=1.0, sigma_0=1.0, nu_0=3.0,
+                 kappa_0=1.0, **kwargs):
+        super(_LatentDistanceWeightsMixin, self).__init__(N, B, dim=dim, sigma_l=sigma_l, L=L, **kwargs)
+        self._shares_L = isinstance(self, _LatentDistanceAdjacencyMixin)
+        if not self._shares_L:
+            self.dim, self.sigma_l = int(dim), float(sigma_l)
+            self.L = self.sigma_l * np.random.randn(N, self.dim) if L is None else np.array(L, dtype=np.float64)
+            assert self.L.shape == (N, self.dim)
+        self.M_0 = np.stack([expand_scalar(mu_0, (B,)), expand_scalar(beta_0, (B,))], axis=1).astype(np.float64)
+        self.V_0 = np.array(expand_cov(v_0, (2, 2)), dtype=np.float64)
+        self.S_0 = np.array(expand_cov(sigma_0, (B, B)), dtype=np.float64)
+        self.nu_0 = float(max(nu_0, B + 2.))
+        self._iw = NIWGaussian(np.zeros(B), self.S_0, 1.0, self.nu_0)          # for its inverse-Wishart sampler
+        self._self_gaussian = NIWGaussian(expand_scalar(mu_0, (B,)), self.S_0, kappa_0, nu_0)
+        self.theta, self.sigma = None, None
+        self._resample_regression(np.zeros((0, 2)), np.zeros((0, B)))           # a draw from the prior
+        self._AW = None
+
+    def sq_distances(self, L=None):
+        L = self.L if L is None else L
+        sq = (L * L).sum(1)
+        return np.maximum(sq[:, None] + sq[None, :] - 2.0 * L.dot(L.T), 0.0)
+
+    def regression_posterior(self, X, Y):
+        """MNIW posterior of (Theta, Sigma) from design rows X (n, 2) = [1, d^2] and weights Y (n, B)."""
+        V0i = np.linalg.inv(self.V_0)
+        Vni = V0i + X.T.dot(X)
+        Vn = np.linalg.inv(Vni)
+        Mn = (self.M_0.dot(V0i) + Y.T.dot(X)).dot(Vn)
+        Sn = self.S_0 + Y.T.dot(Y) + self.M_0.dot(V0i).dot(self.M_0.T) - Mn.dot(Vni).dot(Mn.T)
+        return Mn, Vn, 0.5 * (Sn + Sn.T), self.nu_0 + X.shape[0]
+
+    def _resample_regression(self, X, Y):
+        Mn, Vn, Sn, nun = self.regression_posterior(X, Y)
+        self.sigma = self._iw._sample_invwishart(Sn, nun)
+        Z = np.random.randn(*Mn.shape)
+        self.theta = Mn + np.linalg.cholesky(self.sigma).dot(Z).dot(np.linalg.cholesky(Vn).T)
+
+    @property
+    def mu_W(self):
+        d2 = self.sq_distances()
+        mu = self.theta[:, 0][None, None, :] + d2[:, :, None] * self.theta[:, 1][None, None, :]
+        mu[np.diag_indices(self.N)] = self._self_gaussian.mu
+        return mu
+
+    @property
+    def sigma_W(self):
+        N, B = self.N, self.B
+        sigma = np.repeat(np.reshape(self.sigma, (1, B * B)), N * N, axis=0)
+        sigma[::N + 1] = np.reshape(self._self_gaussian.sigma, (B * B,))
+        return sigma.reshape(N, N, B, B)
+
+    def _weight_location_score(self, n, l):
+        """log p(present weights of row and column n | l_n = l, the rest) up to a constant."""
+        A, W = self._AW
+        diff = self.L - l
+        d2 = np.einsum("md,md->m", diff, diff)
+        tot = 0.0
+        for idx, Wsel in ((A[n], W[n]), (A[:, n], W[:, n])):
+            m = np.flatnonzero(idx)
+            m = m[m != n]
+            if m.size:
+                mean = self.theta[:, 0][None, :] + d2[m, None] * self.theta[:, 1][None, :]
+                tot += _gauss_logpdf(Wsel[m], mean, self.sigma).sum()
+        return float(tot)
+
+    def resample(self, data=[]):
+        A, W = data
+        self._AW = (A, W)
+        off = A & _offdiag(self.N)
+        d2 = self.sq_distances()[off]
+        self._resample_regression(np.stack([np.ones_like(d2), d2], axis=1), W[off])
+        self._self_gaussian.resample(W[np.arange(self.N), np.arange(self.N)][A.diagonal()])
+        if not self._shares_L:
+            for n in np.random.permutation(self.N):
+                self.L[n], _ = elliptical_slice(self.L[n], lambda l, n=n: self._weight_location_score(n, l), self.sigma_l)
+        super(_LatentDistanceWeightsMixin, self).resample(data)
+
+    def get_state(self):
+        s = super(_LatentDistanceWeightsMixin, self).get_state()
+        s["distance_weights"] = dict(theta=self.theta.copy(), sigma=self.sigma.copy(), L=self.L.copy(),
+                                     self_gaussian=self._self_gaussian.get_params())
+        return s
+
+    def set_state(self, state):
+        super(_LatentDistanceWeightsMixin, self).set_state(state)
+        s = state["distance_weights"]
+        self.theta, self.sigma = np.array(s["theta"]), np.array(s["sigma"])
+        self._self_gaussian.set_params(**s["self_gaussian"])
+        if not self._shares_L:
+            self.L = np.array(s["L"])
 
 
 class FixedMeanDenseNetwork(_DenseAdjacencyMixin, _FixedWeightsMixin):
@@ -484,4 +705,32 @@ class FixedMeanStochasticBlockNetwork(_StochasticBlockAdjacencyMixin, _FixedWeig
 
 
 class FixedMeanLatentDistanceNetwork(_LatentDistanceAdjacencyMixin, _FixedWeightsMixin):
+    pass
+
+
+# The paper's full structured models: weights AND adjacency depend on the same latent variables (block labels /
+# locations).  The weight mixin comes first so that its constructor hands C / z (dim / L) on to the adjacency mixin and
+# its resample() runs before the shared latent variables move.
+class StochasticBlockNetwork(_StochasticBlockWeightsMixin, _StochasticBlockAdjacencyMixin):
+    pass
+
+
+class LatentDistanceNetwork(_LatentDistanceWeightsMixin, _LatentDistanceAdjacencyMixin):
+    pass
+
+
+# structured weights over a fixed / dense adjacency prior: the weights alone inform the labels / locations
+class BlockWeightsSparseNetwork(_StochasticBlockWeightsMixin, _FixedAdjacencyMixin):
+    pass
+
+
+class BlockWeightsDenseNetwork(_StochasticBlockWeightsMixin, _DenseAdjacencyMixin):
+    pass
+
+
+class DistanceWeightsSparseNetwork(_LatentDistanceWeightsMixin, _FixedAdjacencyMixin):
+    pass
+
+
+class DistanceWeightsDenseNetwork(_LatentDistanceWeightsMixin, _DenseAdjacencyMixin):
     pass

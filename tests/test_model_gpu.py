@@ -426,7 +426,7 @@ def test_resample_without_data_samples_the_prior():
     assert abs(W_all.mean()) < 0.1 and abs(W_all.std() - 2.0) < 0.1
 
 
-@pytest.mark.parametrize("prior", ["beta_bernoulli", "block", "distance"])
+@pytest.mark.parametrize("prior", ["beta_bernoulli", "block", "distance", "full_block", "full_distance"])
 def test_learned_adjacency_priors_drive_the_scan(prior):
     """the adjacency priors the reference leaves as TODOs (networks.py:175,214,261) as the network
     of a SparseBernoulliGLM: every sweep the host step resamples rho from the current adjacency and the rows reach
@@ -438,7 +438,10 @@ def test_learned_adjacency_priors_drive_the_scan(prior):
     np.random.seed(4)
     net = dict(beta_bernoulli=lambda: networks.NIWBetaBernoulliNetwork(N, B),
                block=lambda: networks.NIWStochasticBlockNetwork(N, B, C=2),
-               distance=lambda: networks.NIWLatentDistanceNetwork(N, B, dim=2))[prior]()
+               distance=lambda: networks.NIWLatentDistanceNetwork(N, B, dim=2),
+               # the paper's full models: block- / distance-dependent weights sharing z / L with the adjacency prior
+               full_block=lambda: networks.StochasticBlockNetwork(N, B, C=2),
+               full_distance=lambda: networks.LatentDistanceNetwork(N, B, dim=2))[prior]()
     m = SparseBernoulliGLM(N, basis=basis, network=net, regression_kwargs=dict(S_w=10.0, mu_b=-2.), seed=6)
     m.add_data(Y)
     ll0 = m.log_likelihood()
