@@ -366,6 +366,8 @@ class GibbsEngine(object):
 
     TC_RECHECK_EVERY = 16       # sweeps between spot checks of the tensor-core Gram against the FP64 kernel
     TC_RECHECK_NEURONS = 2      # neurons compared per spot check (rotating through the local block)
+    TC_RECHECK_TILE_STRIDE = 8  # every 8th (i, j) tile of the FP64 kernel's tile list per check (rotating offset): a check
+                                # costs 1 ms instead of 8 ms at cfg3 and after 8 checks every entry has been compared
 
     def _tc_spot_check(self, ds, omega, n, plan):
         """The first-sweep check (_tc_verified) sees one omega; the deviation of the fixed-point Gram depends on the
@@ -380,7 +382,12 @@ class GibbsEngine(object):
         plan.checks += 1
         om = self._wsbuf("tc_check_omega", (ds.T, pad_ldn(k)), zero=True)
         om[:, :k] = omega[:, lo:lo + k]
-        J_ref = self.K.weighted_gram(ds.Xp, om, self.D, k)
+        tiles = self.K.gram_tiles(self.D, 0)
+        stride = max(1, min(self.TC_RECHECK_TILE_STRIDE, tiles.shape[0]))
+        tiles = tiles[(plan.checks - 1) % stride::stride].contiguous()
+        # entries outside the chosen tiles stay zero in J_ref and are skipped by the comparison below (b != 0)
+        J_ref = self.K.weighted_gram(ds.Xp, om, self.D, k, J=self._wsbuf("tc_check_Jref", (k, self.ldx, self.ldx)).zero_(),
+                                     tiles=tiles)
         J_tc = plan.finalize(self._wsbuf("tc_check_J", (k, self.ldx, self.ldx), zero=True),
                              Jint=plan.Jint[lo:lo + k], omax=plan.omax[lo:lo + k])
         if "tril" not in self._ws:

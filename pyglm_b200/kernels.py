@@ -155,10 +155,13 @@ class CudaKernels(object):
             self._tiles[key] = self.to_device(buf)
         return self._tiles[key]
 
-    def weighted_gram(self, Xp, Om, D, n_valid, J=None, nslabs=None):
-        """J[n, i, j] = sum_t Xp[t,i] Xp[t,j] Om[t,n] on the lower triangle (tile granularity)."""
+    def weighted_gram(self, Xp, Om, D, n_valid, J=None, nslabs=None, tiles=None):
+        """J[n, i, j] = sum_t Xp[t,i] Xp[t,j] Om[t,n] on the lower triangle (tile granularity).
+        tiles: a subset of the rows of gram_tiles(D, 0) (device int32 (k, 2), contiguous) -- only those (i, j) tiles
+        are computed, the rest of J is left as it was."""
         T, ldx = Xp.shape
-        tiles = self.gram_tiles(D, 0)
+        if tiles is None:
+            tiles = self.gram_tiles(D, 0)
         if J is None:
             J = self.zeros(n_valid, ldx, ldx)
         if nslabs is None:
