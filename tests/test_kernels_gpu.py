@@ -533,6 +533,9 @@ def test_marginal_likelihood_kat(K, golden, ss_kernel):
 
 @pytest.mark.parametrize("N,B,T,n_loc,seed", [(6, 2, 400, 6, 0), (27, 3, 3000, 5, 1), (40, 1, 2000, 7, 2),
                                               (12, 4, 1500, 3, 3), (90, 2, 6000, 2, 4),
+                                              # edges: one neuron with a scalar weight (D = 2), B = 5 (beyond the
+                                              # B <= 4 fast / cluster kernels: the generic kernel), two wide blocks
+                                              (1, 1, 300, 1, 6), (3, 5, 900, 3, 7), (2, 4, 500, 2, 8),
                                               # the benchmark's shape: N = 200, B = 2 -> D = 401, active sets of ~280
                                               # coordinates
                                               (200, 2, 20000, 2, 5)])
