@@ -87,7 +87,9 @@ def test_two_rank_sweep_matches_single_process(tmp_path, shard):
         np.testing.assert_allclose(g["mu"], mu0, rtol=1e-12)
 
 
-@pytest.mark.parametrize("prior", ["NIWStochasticBlockNetwork", "NIWLatentDistanceNetwork"])
+@pytest.mark.parametrize("prior", ["NIWStochasticBlockNetwork", "NIWLatentDistanceNetwork",
+                                   # the full structured models: block / distance dependent weights as well
+                                   "StochasticBlockNetwork", "LatentDistanceNetwork"])
 def test_two_rank_chain_with_stateful_network_prior(tmp_path, prior):
     """Block labels / latent locations persist from sweep to sweep: all ranks start from rank 0's network state and
     draw the host step from rank 0's numpy stream, so the sharded chain is the single-process chain."""
