@@ -73,7 +73,7 @@ for n_loc in [int(x) for x in os.environ.get("PROBE_NLOC", "200,100,50,25").spli
     row = dict(n_loc=n_loc, one_cta_ms=t_old)
     for v in os.environ.get("PROBE_VARIANTS", "84,88").split(","):
         t_new, o_new = run(v, n_loc)
-        row["cluster%s_ms" % v[1]] = t_new
+        row[("cluster%s_ms" % v[1]) if len(v) > 1 else ("variant%s_ms" % v)] = t_new
         row["adjacency_equal"] = bool(np.array_equal(o_old[0], o_new[0]))
         row["max_abs_dW"] = float(np.max(np.abs(o_old[1] - o_new[1])))
         row["max_abs_dlogodds"] = float(np.max(np.abs(o_old[3] - o_new[3])))

@@ -1325,9 +1325,12 @@ int dsm_active_clusters_b(int N, int c) {
 }  // namespace
 
 // Which cluster shape, if any, should run n_loc neurons: 0 = none (one CTA per neuron wins).  Estimated time = waves of
-// resident clusters x the per-cluster time measured at cfg3's shape (D = 401, K ~ 250; profiles/r02r_probe_scan_dsm.log):
-// 0.90 ms for 8 CTAs with full rows (13-14 resident), 1.40 ms for 4 CTAs with the lower triangle (~30 resident; its
-// lookahead table is shorter), ~2 ms for 2 CTAs; against 2.4 / 3.1 / 5.0 ms for <= 100 / <= 148 / 200 single-CTA neurons.
+// resident clusters x the per-cluster time measured at cfg3's shape (D = 401) on a state captured at the chain's
+// EQUILIBRIUM density (0.5, K ~ 280; profiles/r02ag_probe_scan.log -- an earlier table measured on the sparse first
+// sweeps underrated the clusters): 1.35 ms for 4 CTAs with the lower triangle (~30 resident; 25 / 50 neurons 1.35 /
+// 2.57 ms), ~1.05 ms for 8 CTAs with full rows (13-14 resident), ~2 ms for 2 CTAs; against 2.9-3.1 ms for <= 100
+// single-CTA neurons, 3.4 for <= 148 and 3.2 per wave beyond.  With these, 50 local neurons (cfg3 on 4 GPUs) run as two
+// waves of 4-CTA clusters: scan 2.86 -> 2.46 ms inside the sweep, 149.1 -> 159.1 sweeps/s (profiles/r02ah_bench_4gpu_*).
 // The ratios, not the absolute values, decide; PYGLM_SS_DSM_MAX_WAVES caps the waves a cluster shape may need (default 2).
 int choose_cluster(const SpikeSlabArgs& A) {
     if (A.B < 1 || A.B > 4 || A.N * A.B + 1 < 24) return 0;
@@ -1335,7 +1338,7 @@ int choose_cluster(const SpikeSlabArgs& A) {
     if (max_waves < 0) { const char* e = getenv("PYGLM_SS_DSM_MAX_WAVES"); max_waves = e ? atoi(e) : 2; }
     static int cap_key = -1, caps[3] = {0, 0, 0};
     const int shapes[3] = {2, 4, 8};
-    const double t_shape[3] = {2.0, 1.4, 0.9};
+    const double t_shape[3] = {2.0, 1.35, 1.05};
     const int key = A.N * 8 + A.B;
     if (key != cap_key) {
         for (int k = 0; k < 3; ++k) {
@@ -1355,7 +1358,7 @@ int choose_cluster(const SpikeSlabArgs& A) {
     // neuron and the smallest one that fits wins by needing the fewest SMs
     const bool small = A.N * A.B + 1 <= 200;
     const int w1 = (A.n_loc + 147) / 148;
-    double best = (A.n_loc <= 100) ? 2.4 : (w1 == 1 ? 3.1 : 2.5 * w1);
+    double best = (A.n_loc <= 100) ? 3.0 : (w1 == 1 ? 3.4 : 3.2 * w1);
     int pick = 0;
     for (int k = 0; k < 3; ++k) {
         if (caps[k] <= 0) continue;
