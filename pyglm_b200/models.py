@@ -162,6 +162,44 @@ class NonlinearAutoregressiveModel(object):
                 return A, W, b
         return self.adjacency, self.weights, self.biases
 
+    # ------------------------------------------------------------------ checkpoint / resume (optional)
+    def state_dict(self):
+        """Everything a chain needs to continue bit for bit: the sampler state (A, W, b, eta), the hyper-parameters the
+        regressions currently hold, the network's latent state, the engine's Philox seed and sweep counter and numpy's
+        global RNG state (the host network step draws from it).  O(N^2 B) numbers; the data are not included.  The
+        reference has no checkpointing (its state is the same plain attributes)."""
+        eng = self.engine
+        A, W, b = self._host_state()
+        regs = self.regressions
+        net = getattr(self, "network", None)
+        hyp = self._stacked_hypers()
+        return dict(version=1, N=self.N, B=self.B, seed=int(eng.seed), calls=int(eng.calls),
+                    rng=np.random.get_state(), A=np.array(A), W=np.array(W), b=np.array(b),
+                    eta=[getattr(r, "eta", None) for r in regs],
+                    hypers={k: np.array(v) for k, v in hyp.items()},
+                    network=net.get_state() if hasattr(net, "get_state") else None)
+
+    def load_state_dict(self, sd):
+        """Continue the chain a state_dict() was taken from: same model structure (N, B, network class) and the same
+        data added in the same order.  Restores numpy's GLOBAL RNG state."""
+        assert sd["version"] == 1 and sd["N"] == self.N and sd["B"] == self.B, "state_dict of a different model"
+        eng = self.engine
+        eng.seed, eng.calls = int(sd["seed"]), int(sd["calls"])
+        eng._pending = None                         # a pre-launched augmentation belongs to the old sweep counter
+        for n, r in enumerate(self.regressions):
+            r.a, r.W, r.b = sd["A"][n].copy(), sd["W"][n].copy(), sd["b"][n:n + 1].copy()
+            if sd["eta"][n] is not None:
+                r.eta = sd["eta"][n]
+            h = sd["hypers"]
+            r.rho, r.mu_w, r.S_w = h["rho"][n].copy(), h["mu_w"][n].copy(), h["S_w"][n].copy()
+            r.mu_b, r.S_b = h["mu_b"][n], h["S_b"][n]
+        self._state_src = self._hyper_src = None
+        net = getattr(self, "network", None)
+        if sd["network"] is not None and hasattr(net, "set_state"):
+            net.set_state(sd["network"])
+        self._ranks_synced = True                   # every rank loads the same dictionary
+        np.random.set_state(sd["rng"])
+
     # ------------------------------------------------------------------ data (models.py:66-80)
     def add_data(self, data, X=None, host_X=True, slab=None):
         """Append a (T, N) spike matrix.  X (T, N, B) may be supplied; otherwise it is the causal convolution of

@@ -373,6 +373,47 @@ def test_overlapped_sweeps_switch_modes_mid_chain():
         assert np.array_equal(A1, A2) and np.array_equal(W1, W2) and np.array_equal(b1, b2)
 
 
+@pytest.mark.parametrize("prior", ["niw", "full_block"])
+def test_checkpointed_chain_resumes_bit_for_bit(prior):
+    """state_dict() / load_state_dict() (optional row): the chain continued from a checkpoint -- in the same
+    model, whose pre-launched augmentation of the next sweep must be dropped, and in a freshly built one -- equals the
+    uninterrupted chain exactly: Philox seed + sweep counter, numpy's RNG state, (A, W, b), hyper-parameters and the
+    network's latent state are all the randomness there is."""
+    from pyglm_b200 import networks
+    from pyglm_b200.models import SparseBernoulliGLM
+    from pyglm_b200.utils.basis import cosine_basis
+    N, B, L, T = 9, 2, 20, 4000
+    basis = cosine_basis(B, L=L) / L
+    Y = (np.random.default_rng(5).random((T, N)) < 0.08).astype(np.float64)
+
+    def build(np_seed, seed):
+        np.random.seed(np_seed)
+        net = networks.StochasticBlockNetwork(N, B, C=2) if prior == "full_block" else None
+        m = SparseBernoulliGLM(N, basis=basis, network=net, regression_kwargs=dict(S_w=10.0, mu_b=-2.0), seed=seed)
+        m.add_data(Y)
+        return m
+
+    def run(m, n):
+        out = []
+        for _ in range(n):
+            m.resample_model()
+            out.append((m.adjacency.copy(), m.weights.copy(), m.biases.copy(), m.log_likelihood()))
+        return out
+
+    m = build(0, 21)
+    run(m, 3)
+    sd = m.state_dict()
+    ref = run(m, 3)
+    m.load_state_dict(sd)
+    again = run(m, 3)
+    other = build(99, 1234)
+    other.load_state_dict(sd)
+    fresh = run(other, 3)
+    for got in (again, fresh):
+        for (A1, W1, b1, l1), (A2, W2, b2, l2) in zip(ref, got):
+            assert np.array_equal(A1, A2) and np.array_equal(W1, W2) and np.array_equal(b1, b2) and l1 == l2
+
+
 @pytest.mark.parametrize("pipeline", [True, False])
 def test_device_moments_match_host_collection(pipeline):
     """running moments of the samples kept in HBM equal what the reference's example loop collects on
