@@ -6,7 +6,7 @@
 The public attributes and call signatures are the reference's (models.py:28-236); what changes is where the
 work happens: add_data filters on the GPU, resample_model runs one GibbsEngine.sweep for all N regressions at
 once (the reference loops over them, models.py:169-171), and log_likelihood / means are single fused kernels.
-Extra keyword-only arguments (`seed`, `shard`, `gram`) default to reference behaviour.
+Extra keyword-only arguments (`seed`, `shard`, `gram` / `precision`, `device`) default to reference behaviour.
 """
 import numpy as np
 
@@ -38,7 +38,14 @@ class NonlinearAutoregressiveModel(object):
     (models.py:8-201)."""
 
     def __init__(self, N, regressions, basis=None, B=10, seed=None, shard="neuron", comm=None, gram="auto",
-                 gram_stream="auto"):
+                 gram_stream="auto", precision=None, device=None):
+        # precision: SURVEY 5's name for the Gram arithmetic -- "fp64" (FP64 DMMA kernel), "int8" (tcgen05 integer-digit
+        # kernel, exact integer sums, <= 1e-9 of FP64) or "auto"; an alias of `gram`.  device: CUDA device (index or
+        # torch.device) of this process' engine; default: the current device (one process per GPU).
+        if precision is not None:
+            assert gram == "auto", "give either gram= or precision=, not both"
+            gram = {"fp64": "fp64", "int8": "tc", "tc": "tc", "auto": "auto"}[precision]
+        self._device = device
         self.N = N
         assert len(regressions) == N
         self.regressions = regressions
@@ -75,9 +82,14 @@ class NonlinearAutoregressiveModel(object):
     @property
     def engine(self):
         if self._engine is None:
-            from .engine import GibbsEngine
-            self._engine = GibbsEngine(self.N, self.B, seed=self._seed, comm=self._comm, shard=self._shard,
-                                       gram=self._gram, gram_stream=self._gram_stream)
+            from .engine import GibbsEngine, default_kernels
+            kernels = None
+            if self._device is not None:
+                import torch
+                dev = self._device if isinstance(self._device, torch.device) else torch.device("cuda", int(self._device))
+                kernels = default_kernels(dev)
+            self._engine = GibbsEngine(self.N, self.B, kernels=kernels, seed=self._seed, comm=self._comm,
+                                       shard=self._shard, gram=self._gram, gram_stream=self._gram_stream)
         return self._engine
 
     def _sync_ranks(self):

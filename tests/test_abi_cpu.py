@@ -99,6 +99,12 @@ def test_host_api_without_gpu(golden):
     assert np.all(m.weights[~m.adjacency] == 0)
     with pytest.raises(AssertionError):
         r.S_b = np.eye(1)                      # S_b must be a scalar (regression.py:135)
+    # SURVEY 5's keyword extras: precision= is an alias of gram=, device= picks the engine's GPU (nothing is created here)
+    m2 = SparseBernoulliGLM(N, basis=cosine_basis(B, 20) / 20, precision="int8", device=0, seed=3)
+    assert m2._gram == "tc" and m2._device == 0 and m2._engine is None
+    assert SparseBernoulliGLM(N, basis=cosine_basis(B, 20) / 20, precision="fp64")._gram == "fp64"
+    with pytest.raises(AssertionError):
+        SparseBernoulliGLM(N, basis=cosine_basis(B, 20) / 20, precision="fp64", gram="tc")
     # prior terms against the oracle's dense prior statistics
     rng = np.random.default_rng(1)
     S_w = np.stack([[np.eye(B) * rng.uniform(0.5, 3) + 0.1 for _ in range(N)] for _ in range(3)])
