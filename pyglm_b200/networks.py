@@ -32,12 +32,15 @@ class NIWGaussian(object):
         n = data.shape[0]
         if n == 0:
             return self.mu_0, self.sigma_0, self.kappa_0, self.nu_0
-        xbar = data.mean(axis=0)
-        dev = data - xbar
+        # on the transposed copy (D contiguous rows of n numbers): reductions along the long axis of an (n, D) array
+        # with D = 1..4 are several times slower, and this runs between two sweeps on the host (18 000 rows at cfg3)
+        dt = np.ascontiguousarray(data.T)
+        xbar = dt.sum(axis=1) / n
+        dt -= xbar[:, None]
         kappa_n = self.kappa_0 + n
         mu_n = (self.kappa_0 * self.mu_0 + n * xbar) / kappa_n
         d0 = xbar - self.mu_0
-        sigma_n = self.sigma_0 + dev.T.dot(dev) + (self.kappa_0 * n / kappa_n) * np.outer(d0, d0)
+        sigma_n = self.sigma_0 + dt.dot(dt.T) + (self.kappa_0 * n / kappa_n) * np.outer(d0, d0)
         return mu_n, sigma_n, kappa_n, self.nu_0 + n
 
     def _sample_invwishart(self, S, nu):
