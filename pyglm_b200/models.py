@@ -415,7 +415,8 @@ class HierarchicalNonlinearAutoregressiveModel(NonlinearAutoregressiveModel):
         # identical draws on every rank -- no per-sweep host collective on the critical path between two scans.
         if self._engine is not None:
             self._sync_ranks()
-        net.resample((self.adjacency, self.weights))
+        A, W, _ = self._host_state()                 # the stacked arrays of the last sweep, not rebuilt row by row
+        net.resample((np.asarray(A, dtype=bool), np.asarray(W)))
         sigma_W, mu_W, rho = net.sigma_W, net.mu_W, net.rho
         N, B = self.N, self.B
         fast = (sigma_W.shape == (N, N, B, B) and mu_W.shape == (N, N, B) and rho.shape == (N, N)
