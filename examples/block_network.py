@@ -5,6 +5,7 @@ connection probabilities and the NIW weight prior are resampled on the host afte
 inclusion prior rho of the spike-and-slab scan (pyglm/models.py:228-236).
 
     python examples/block_network.py [--N 16] [--T 200000] [--sweeps 100] [--prior block|distance|beta_bernoulli]
+                                     [--weights fixed|niw|structured]
 """
 import argparse
 import os
@@ -22,9 +23,11 @@ ap.add_argument("--N", type=int, default=16)
 ap.add_argument("--T", type=int, default=200000)
 ap.add_argument("--sweeps", type=int, default=100)
 ap.add_argument("--prior", default="block", choices=["block", "distance", "beta_bernoulli"])
-ap.add_argument("--weights", default="fixed", choices=["fixed", "niw"],
-                help="fixed N(0, 1) slab, or the learned NIW slab (under which weak and absent connections are hard "
-                     "to tell apart, so the graph -- and with it the block structure -- stays diffuse)")
+ap.add_argument("--weights", default="fixed", choices=["fixed", "niw", "structured"],
+                help="fixed N(0, 1) slab; the learned NIW slab (under which weak and absent connections are hard "
+                     "to tell apart, so the graph -- and with it the block structure -- stays diffuse); or the paper's "
+                     "full model, in which the weights depend on the same block labels / locations as the adjacency "
+                     "(networks.StochasticBlockNetwork / LatentDistanceNetwork)")
 args = ap.parse_args()
 np.random.seed(0)
 N, T, B, L = args.N, args.T, 1, 50
@@ -43,7 +46,11 @@ _, Y = true_model.generate(T=T, keep=True)
 print("simulated %d bins x %d neurons, mean rate %.3f" % (T, N, Y.mean()))
 
 cls = dict(block="StochasticBlockNetwork", distance="LatentDistanceNetwork", beta_bernoulli="BetaBernoulliNetwork")
-cls = getattr(networks, ("FixedMean" if args.weights == "fixed" else "NIW") + cls[args.prior])
+if args.weights == "structured":
+    assert args.prior != "beta_bernoulli", "the Beta-Bernoulli prior has no latent structure for the weights to share"
+    cls = getattr(networks, cls[args.prior])
+else:
+    cls = getattr(networks, ("FixedMean" if args.weights == "fixed" else "NIW") + cls[args.prior])
 net = cls(N, B, **(dict(C=2) if args.prior == "block" else dict(dim=2) if args.prior == "distance" else {}))
 model = SparseBernoulliGLM(N, basis=basis, network=net, regression_kwargs=dict(S_w=1.0, mu_b=-3.0))
 model.add_data(Y)
