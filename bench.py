@@ -344,7 +344,7 @@ def main():
     e2e_ms = ev0.elapsed_time(ev1) / steps
     h2d = (eng.h2d_bytes - h2d0) // steps
     d2h = (eng.d2h_bytes - d2h0) // steps
-    launches = (K.launches - l0) // steps
+    launches = K.launches - l0                           # our kernels launched inside the timed region (e2e loop)
 
     # ---- `value`: whole sweeps with inputs resident in HBM (the engine call), with every kernel phase timed by
     # CUDA events on the launching stream inside the same timed region -------------------------------------
@@ -456,7 +456,7 @@ def main():
                         l2="inputs (X %.0f MB, omega %.0f MB%s per rank) exceed the 126 MB L2"
                            % (ds.Xp.numel() * 8 / 1e6, T_loc * eng.K.lib_ldn(n_loc) * 8 / 1e6, resident), **cfg),
             e2e=dict(value=1e3 / e2e_ms, unit="sweeps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
-            gpu_launches=int(launches),
+            gpu_launches=int(launches), gpu_launches_per_step=int(launches // steps),
             roofline=roof,
             kernels_ms=kern_ms,
             dominant_kernel=max((k for k in kern_ms if not k.startswith("gram_")), key=lambda k: kern_ms[k]),
