@@ -215,7 +215,9 @@ def run_reference(args, cfg, name):
     else:
         desc = ("1 of %d regressions per step on the first %d of T=%d bins (%d timed in all): psi / PG / dgemm Gram "
                 "scaled by T/T_s, a-scan and W draw measured in full; sweep = N x their mean" % (N, T_s, T, len(per_reg)))
-    line = dict(metric="gibbs_sweeps_per_sec", value=val, unit="sweeps/s", n_gpus=0, steps=steps,
+    # n_gpus mirrors the --gpus the arm was launched with (the driver pairs the two arms by it); the reference's path
+    # runs on the host cores only
+    line = dict(metric="gibbs_sweeps_per_sec", value=val, unit="sweeps/s", n_gpus=int(args.gpus), gpus_used=0, steps=steps,
                 warmup=warmup, ms_per_step=sweep_s * 1e3,
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                 impl="reference", config=dict(workload=name, **cfg),
