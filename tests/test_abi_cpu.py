@@ -123,3 +123,30 @@ def test_host_api_without_gpu(golden):
             c = 0.5 * np.linalg.slogdet(J0[blk, blk])[1] - 0.5 * h0[blk] @ np.linalg.solve(J0[blk, blk], h0[blk])
             assert pr["cprior"][j, mth] == pytest.approx(c, rel=1e-12, abs=1e-14)
         assert pr["J0b"][j] == pytest.approx(J0[-1, -1]) and pr["h0b"][j] == pytest.approx(h0[-1])
+
+
+@pytest.mark.parametrize("B", [1, 2, 3])
+def test_prior_terms_closed_forms_equal_the_lapack_route(B):
+    """priors.prior_arrays takes closed forms on contiguous planes for B <= 2 (it runs on the host between two sweeps)
+    and numpy's batched inv / slogdet beyond: both must give regression.py:138-151, 210-223 for non-isotropic blocks."""
+    from pyglm_b200.priors import prior_arrays
+    rng = np.random.default_rng(B)
+    n, N = 4, 7
+    M = rng.standard_normal((n, N, B, B))
+    S_w = M @ M.transpose(0, 1, 3, 2) + 0.3 * np.eye(B)
+    mu_w = rng.standard_normal((n, N, B))
+    rho = rng.uniform(0.05, 0.95, (n, N))
+    rho[1] = 1.0                                             # a deterministic row: no scan (regression.py:153-155)
+    pr = prior_arrays(rho, mu_w, S_w, rng.standard_normal(n), rng.uniform(0.5, 2.0, n))
+    J = np.linalg.inv(S_w)
+    h = np.einsum("nmbc,nmc->nmb", J, mu_w)
+    sign, logdet = np.linalg.slogdet(J)
+    np.testing.assert_allclose(pr["J0w"], J, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(pr["h0w"], h, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(pr["cprior"], 0.5 * logdet - 0.5 * np.einsum("nmb,nmb->nm", mu_w, h), rtol=1e-12, atol=1e-13)
+    assert list(pr["do_scan"]) == [True, False, True, True]
+    assert pr["J0w"].flags.c_contiguous and pr["h0w"].flags.c_contiguous
+    bad = S_w.copy()
+    bad[2, 3] = -np.eye(B)
+    with pytest.raises(ValueError):
+        prior_arrays(rho, mu_w, bad, np.zeros(n), np.ones(n))
